@@ -1,0 +1,162 @@
+/*
+ * tensorrec_b200.h -- C ABI of the B200-native predict / predict_rank hot path of jfkirk/tensorrec.
+ *
+ * The reference (pure Python over TensorFlow 1.x, commit 80690737) has no FFI of its own; the boundary a
+ * maintainer would bind is the set of TF ops its graph evaluates on this path.  Each entry point below
+ * replaces one of those graph nodes (reference file:line given per function; paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns every buffer;
+ *   - matrices are dense row-major; indices are int32; values float32;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous;
+ *   - return value: 0 = ok, negative = TRK_ERR_*; trk_last_error() gives the text for this thread;
+ *   - nothing here allocates persistent device memory; workspace sizes are queried and caller-provided;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns TRK_ERR_CUDA.
+ */
+#ifndef TENSORREC_B200_H_
+#define TENSORREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRK_OK 0
+#define TRK_ERR_ARG (-1)         /* bad argument (null pointer, size, alignment, unsupported shape) */
+#define TRK_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define TRK_ERR_UNSUPPORTED (-3) /* shape outside what the fused tensor-core kernel supports */
+
+/* ABI version of this header (major*1000 + minor). */
+int trk_version(void);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* trk_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K1  sparse features -> dense representation (CSR x dense gather-reduce)
+ *
+ * replaces tf.sparse_tensor_dense_matmul in LinearRepresentationGraph.connect_representation_graph
+ * (tensorrec/representation_graphs.py:32-43, the matmul is :40) and, with n_normalize >= 1, the
+ * tf.nn.l2_normalize of NormalizedLinearRepresentationGraph (:53-58, :57) and of relative_cosine
+ * (tensorrec/recommendation_graphs.py:119-120).
+ *
+ *   out[r, :] = sum over p in [indptr[r], indptr[r+1])  val[p] * weights[col[p], :]     (fp32, CSR order)
+ *   then n_normalize times:  out[r, :] *= rsqrt(max(sum(out[r, :]^2), 1e-12))
+ *
+ * CSR entries of one row are accumulated sequentially in storage order (duplicates are summed), so the
+ * result is run-to-run bit-identical (reference requirement: test/test_tensorrec.py:418-458).
+ *
+ * Outputs (either may be NULL, not both):
+ *   out_f32   [rows, d]            the representation as the reference returns it;
+ *   out_split [rows, 2*d_pad] f16  the operand layout of the tensor-core score kernel: columns [0,d_pad) hold
+ *                                  hi = fp16(x * 2^e_r), columns [d_pad, 2*d_pad) hold lo = fp16(x * 2^e_r - hi),
+ *                                  zero padded from d to d_pad (d_pad a multiple of 64);
+ *   out_scale [rows]               2^-e_r, the exact power of two that undoes the per-row scaling
+ *                                  (required when out_split is given).
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const float* val,
+                              const float* weights, int64_t rows, int32_t n_features, int32_t d,
+                              int32_t n_normalize, float* out_f32, void* out_split, int32_t d_pad,
+                              float* out_scale, void* stream);
+
+/* Converts an existing dense fp32 representation [rows, d] into the split-fp16 operand + scales
+ * (same layout as above).  Used when a representation comes from a user-defined plugin graph. */
+int trk_split_f32_to_f16x2(const float* repr, int64_t rows, int32_t d, int32_t n_normalize, void* out_split,
+                           int32_t d_pad, float* out_scale, void* stream);
+
+/* L2-normalises rows of a dense fp32 matrix in place: tf.nn.l2_normalize(x, 1)
+ * (tensorrec/recommendation_graphs.py:119-120). */
+int trk_l2_normalize_rows_f32(float* x, int64_t rows, int32_t d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * project_biases (tensorrec/recommendation_graphs.py:4-19):
+ *   out[r] = sum over the row's entries  val[p] * feature_biases[col[p]]      (fp32, CSR order)
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_csr_project_biases_f32(const int32_t* indptr, const int32_t* col, const float* val,
+                               const float* feature_biases, int64_t rows, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K2 (exact fp32, CUDA cores)  dense prediction for every user x item pair, any shape
+ *
+ * replaces tf.matmul(user, item, transpose_b=True) of DotProductPredictionGraph.connect_dense_prediction_graph
+ * (tensorrec/prediction_graphs.py:49-50) / relative_cosine (tensorrec/recommendation_graphs.py:121, inputs
+ * pre-normalised by K1), followed by collapse_mixture_of_tastes without attention (max over tastes,
+ * tensorrec/recommendation_graphs.py:107) and bias_prediction_dense (:41):
+ *
+ *   out[u, i] = max_t ( sum_k user_repr[t, u, k] * item_repr[i, k] )  + user_bias[u] + item_bias[i]
+ *
+ * user_repr is [n_tastes, n_users, d]; user_bias / item_bias may be NULL (unbiased model).
+ * mode: 0 = dot product, 1 = negative euclidean distance (EuclideanSimilarityPredictionGraph,
+ * tensorrec/prediction_graphs.py:84-100).
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_score_f32(const float* user_repr, const float* item_repr, const float* user_bias,
+                  const float* item_bias, float* out, int64_t n_users, int64_t n_items, int32_t d,
+                  int32_t n_tastes, int32_t mode, void* stream);
+
+/* Attention variant of the taste collapse (tensorrec/recommendation_graphs.py:96-103):
+ *   out[u,i] = sum_t softmax_t(att[t,u,i]) * pred[t,u,i]  (+ biases), pred/att = dot products of
+ *   user_repr[t] / attention_repr[t] with item_repr. */
+int trk_score_attention_f32(const float* user_repr, const float* attention_repr, const float* item_repr,
+                            const float* user_bias, const float* item_bias, float* out, int64_t n_users,
+                            int64_t n_items, int32_t d, int32_t n_tastes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K3 (full)  rank_predictions (tensorrec/recommendation_graphs.py:73-82): the reference's double
+ * tf.nn.top_k(k = n_items) == for every user row
+ *     rank[u, i] = 1 + #{j : s[u,j] > s[u,i]} + #{j < i : s[u,j] == s[u,i]}          (int32, 1-based)
+ * computed by a per-row sort of (score descending, index ascending) keys.
+ * workspace: trk_rank_full_workspace_bytes(n_users, n_items) bytes of device memory.
+ * ---------------------------------------------------------------------------------------------------- */
+size_t trk_rank_full_workspace_bytes(int64_t n_users, int64_t n_items);
+int trk_rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_items, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * K2+K3 fused (tensor cores, sm_100a)  scores and per-user top-k without materialising [n_users, n_items]
+ *
+ * replaces the chain  tf.matmul (prediction_graphs.py:49-50)  ->  bias_prediction_dense
+ * (recommendation_graphs.py:41)  ->  rank_predictions (recommendation_graphs.py:73-82) restricted to the
+ * entries with rank <= k (the only ones tensorrec/eval.py:23,49,68-69 ever reads).
+ *
+ * Operands are the split-fp16 layout produced by K1 (hi/lo halves, per-row power-of-two scale); the score is
+ *   s[u,i] = (hi_u.hi_i + hi_u.lo_i + lo_u.hi_i) * scale_u * scale_i + user_bias[u] + item_bias[i]
+ * accumulated in fp32 in tensor memory (three tcgen05.mma passes per k-block; relative error vs an fp32 dot
+ * product <= 2^-21 of |u|.|i|, and exact for integer-valued representations).
+ *
+ * The item axis is cut into n_splits contiguous ranges (parallelism when n_users is small; shards when the
+ * item axis is distributed over GPUs).  For each (user, split) the kernel emits the k best candidates ordered by
+ * (score descending, item id ascending):
+ *   cand_score [n_users, n_splits, k] f32,  cand_item [n_users, n_splits, k] i32 (GLOBAL ids = local + item_id_offset;
+ *   unused slots: score = -inf, id = INT32_MAX).
+ * item_meta [n_items_padded256, 2] f32 = {item scale, item bias} per item, rows beyond n_items = {0, -inf}
+ * (build with trk_pack_item_meta).  user_bias may be NULL.
+ * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_topk_max_k(d_pad).
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_score_topk_max_k(int32_t d_pad);
+int trk_pack_item_meta(const float* item_scale, const float* item_bias, int64_t n_items, float* item_meta,
+                       int64_t n_items_padded, void* stream);
+int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
+                         const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
+                         int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset,
+                         float* cand_score, int32_t* cand_item, void* stream);
+
+/* Tensor-core dense prediction with the same operands, writing the full fp32 matrix out[n_users, n_items]
+ * (predict(); tensorrec/tensorrec.py:636-664).  HBM-write bound. */
+int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
+                          const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
+                          int32_t d_pad, float* out, int64_t out_row_stride, void* stream);
+
+/* Merges n_lists candidate lists per user (each sorted by (score desc, id asc), k_in entries) into the global
+ * top k_out per user, same order.  Lists are the n_splits of one GPU and/or the shards gathered from the
+ * other GPUs (item-axis sharding; the exchange itself is one NCCL all-gather done by the host layer).
+ *   cand_* [n_users, n_lists, k_in]  ->  out_* [n_users, k_out] */
+int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
+                   int32_t k_in, int32_t k_out, float* out_score, int32_t* out_item, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSORREC_B200_H_ */

@@ -1,0 +1,132 @@
+// extern "C" entry points declared in include/tensorrec_b200.h (plain pointers and sizes, no torch types).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace trk {
+
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kSMsB200;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMsB200;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// implemented in the kernel translation units
+int csr_gather_reduce(const int32_t*, const int32_t*, const float*, const float*, int64_t, int32_t, int32_t, int32_t,
+                      float*, void*, int32_t, float*, cudaStream_t);
+int split_rows(const float*, int64_t, int32_t, int32_t, float*, void*, int32_t, float*, cudaStream_t);
+int csr_project_biases(const int32_t*, const int32_t*, const float*, const float*, int64_t, float*, cudaStream_t);
+int pack_item_meta(const float*, const float*, int64_t, float*, int64_t, cudaStream_t);
+int score_f32(const float*, const float*, const float*, const float*, const float*, float*, int64_t, int64_t, int32_t,
+              int32_t, int32_t, cudaStream_t);
+int l2_normalize_rows(float*, int64_t, int32_t, cudaStream_t);
+size_t rank_full_workspace_bytes(int64_t, int64_t);
+int rank_full(const float*, int32_t*, int64_t, int64_t, void*, size_t, cudaStream_t);
+int score_topk_max_k(int32_t);
+int score_topk_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
+                     int32_t, int32_t, int32_t, float*, int32_t*, cudaStream_t);
+int score_dense_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
+                      float*, int64_t, cudaStream_t);
+int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t, float*, int32_t*, cudaStream_t);
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+}  // namespace trk
+
+extern "C" {
+
+int trk_version(void) { return 1000; }
+
+const char* trk_last_error(void) { return trk::g_last_error; }
+
+int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const float* val, const float* weights,
+                              int64_t rows, int32_t n_features, int32_t d, int32_t n_normalize, float* out_f32,
+                              void* out_split, int32_t d_pad, float* out_scale, void* stream) {
+  return trk::csr_gather_reduce(indptr, col, val, weights, rows, n_features, d, n_normalize, out_f32, out_split,
+                                d_pad, out_scale, trk::as_stream(stream));
+}
+
+int trk_split_f32_to_f16x2(const float* repr, int64_t rows, int32_t d, int32_t n_normalize, void* out_split,
+                           int32_t d_pad, float* out_scale, void* stream) {
+  TRK_CHECK_ARG(out_split != nullptr, "trk_split_f32_to_f16x2: null output");
+  return trk::split_rows(repr, rows, d, n_normalize, nullptr, out_split, d_pad, out_scale, trk::as_stream(stream));
+}
+
+int trk_l2_normalize_rows_f32(float* x, int64_t rows, int32_t d, void* stream) {
+  return trk::l2_normalize_rows(x, rows, d, trk::as_stream(stream));
+}
+
+int trk_csr_project_biases_f32(const int32_t* indptr, const int32_t* col, const float* val,
+                               const float* feature_biases, int64_t rows, float* out, void* stream) {
+  return trk::csr_project_biases(indptr, col, val, feature_biases, rows, out, trk::as_stream(stream));
+}
+
+int trk_score_f32(const float* user_repr, const float* item_repr, const float* user_bias, const float* item_bias,
+                  float* out, int64_t n_users, int64_t n_items, int32_t d, int32_t n_tastes, int32_t mode,
+                  void* stream) {
+  return trk::score_f32(user_repr, nullptr, item_repr, user_bias, item_bias, out, n_users, n_items, d, n_tastes,
+                        mode, trk::as_stream(stream));
+}
+
+int trk_score_attention_f32(const float* user_repr, const float* attention_repr, const float* item_repr,
+                            const float* user_bias, const float* item_bias, float* out, int64_t n_users,
+                            int64_t n_items, int32_t d, int32_t n_tastes, void* stream) {
+  TRK_CHECK_ARG(attention_repr != nullptr, "trk_score_attention_f32: null attention representation");
+  return trk::score_f32(user_repr, attention_repr, item_repr, user_bias, item_bias, out, n_users, n_items, d,
+                        n_tastes, 0, trk::as_stream(stream));
+}
+
+size_t trk_rank_full_workspace_bytes(int64_t n_users, int64_t n_items) {
+  return trk::rank_full_workspace_bytes(n_users, n_items);
+}
+
+int trk_rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_items, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  return trk::rank_full(scores, ranks, n_users, n_items, workspace, workspace_bytes, trk::as_stream(stream));
+}
+
+int trk_score_topk_max_k(int32_t d_pad) { return trk::score_topk_max_k(d_pad); }
+
+int trk_pack_item_meta(const float* item_scale, const float* item_bias, int64_t n_items, float* item_meta,
+                       int64_t n_items_padded, void* stream) {
+  return trk::pack_item_meta(item_scale, item_bias, n_items, item_meta, n_items_padded, trk::as_stream(stream));
+}
+
+int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
+                         const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
+                         int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset, float* cand_score,
+                         int32_t* cand_item, void* stream) {
+  return trk::score_topk_f16x3(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, k,
+                               n_splits, item_id_offset, cand_score, cand_item, trk::as_stream(stream));
+}
+
+int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
+                          const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
+                          int32_t d_pad, float* out, int64_t out_row_stride, void* stream) {
+  return trk::score_dense_f16x3(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad,
+                                out, out_row_stride, trk::as_stream(stream));
+}
+
+int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
+                   int32_t k_in, int32_t k_out, float* out_score, int32_t* out_item, void* stream) {
+  return trk::topk_merge(cand_score, cand_item, n_users, n_lists, k_in, k_out, out_score, out_item,
+                         trk::as_stream(stream));
+}
+
+}  // extern "C"

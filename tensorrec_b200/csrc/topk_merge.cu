@@ -1,0 +1,89 @@
+// Merge of per-(user, list) top-k candidate lists into the global per-user top-k.
+//
+// Lists come from the n_splits item ranges of one GPU and/or from the item shards of the other GPUs (gathered by
+// one NCCL all-gather in the host layer).  Every list is ordered by (score descending, item id ascending) -- the
+// order tf.nn.top_k gives the reference (tensorrec/recommendation_graphs.py:81) -- and padded with
+// (-inf, INT32_MAX).  One warp per user performs an n_lists-way merge: lane l holds the heads of lists l, l+32, ...;
+// each of the k_out rounds is a warp arg-best over the heads.  Integer/float compares only: deterministic.
+#include "common.cuh"
+
+namespace trk {
+
+constexpr int kMergeMaxListsPerLane = 8;  // n_lists <= 256
+
+__device__ __forceinline__ bool cand_better(float s, int32_t i, float bs, int32_t bi) {
+  return s > bs || (s == bs && i < bi);
+}
+
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_item, int64_t n_users,
+                  int n_lists, int k_in, int k_out, float* __restrict__ out_score, int32_t* __restrict__ out_item) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * blockDim.x / 32;
+  const float kNegInf = -__int_as_float(0x7f800000);
+  for (int64_t u = warp; u < n_users; u += n_warps) {
+    const float* cs = cand_score + u * n_lists * k_in;
+    const int32_t* ci = cand_item + u * n_lists * k_in;
+    int pos[kMergeMaxListsPerLane];
+#pragma unroll
+    for (int j = 0; j < kMergeMaxListsPerLane; ++j) pos[j] = 0;
+    for (int round = 0; round < k_out; ++round) {
+      float bs = kNegInf;
+      int32_t bi = 0x7fffffff;
+      int bj = -1;
+#pragma unroll
+      for (int j = 0; j < kMergeMaxListsPerLane; ++j) {
+        const int l = lane + 32 * j;
+        if (l < n_lists && pos[j] < k_in) {
+          const float s = cs[l * k_in + pos[j]];
+          const int32_t i = ci[l * k_in + pos[j]];
+          if (cand_better(s, i, bs, bi)) {
+            bs = s;
+            bi = i;
+            bj = j;
+          }
+        }
+      }
+      float ws = bs;
+      int32_t wi = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+        const int32_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (cand_better(os, oi, ws, wi)) {
+          ws = os;
+          wi = oi;
+        }
+      }
+      // real candidates have unique ids; the owner of the winner advances its list head
+      if (bj >= 0 && wi != 0x7fffffff && bs == ws && bi == wi) {
+#pragma unroll
+        for (int j = 0; j < kMergeMaxListsPerLane; ++j)
+          if (j == bj) pos[j] += 1;
+      }
+      if (lane == 0) {
+        out_score[u * k_out + round] = ws;
+        out_item[u * k_out + round] = wi;
+      }
+    }
+  }
+}
+
+int topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists, int32_t k_in,
+               int32_t k_out, float* out_score, int32_t* out_item, cudaStream_t stream) {
+  TRK_CHECK_ARG(cand_score && cand_item && out_score && out_item, "topk_merge: null pointer");
+  TRK_CHECK_ARG(n_users >= 0 && n_lists >= 1 && k_in >= 1 && k_out >= 1, "topk_merge: bad sizes");
+  TRK_CHECK_ARG(n_lists <= 32 * kMergeMaxListsPerLane, "topk_merge: n_lists=%d exceeds %d", n_lists,
+                32 * kMergeMaxListsPerLane);
+  if (n_users == 0) return TRK_OK;
+  const int threads = 256;
+  const int64_t blocks = ceil_div(n_users, threads / 32);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  topk_merge_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
+      cand_score, cand_item, n_users, n_lists, k_in, k_out, out_score, out_item);
+  TRK_CHECK_LAUNCH();
+  return TRK_OK;
+}
+
+}  // namespace trk

@@ -1,0 +1,249 @@
+"""Host-side launch layer: torch supplies device memory and streams, every computation is a call through the C ABI
+(libtensorrec_b200.so).  No function here has a CPU path; all of them raise without a CUDA device."""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+
+TILE_ITEMS = 256     # item tile of the tensor-core kernel (item_meta is padded to a multiple of this)
+TILE_USERS = 128
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('tensorrec_b200 runs its predict / predict_rank path on a CUDA device (B200, sm_100a) only; '
+                           'no CUDA device is visible and there is no CPU fallback')
+    return _lib.load()
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, device):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def d_pad_for(n_components):
+    """Width of the split-fp16 operand: n_components rounded up to the 64-element swizzle row."""
+    return ((int(n_components) + 63) // 64) * 64
+
+
+class DeviceCSR(object):
+    """Sparse features resident in HBM as CSR: int32 indptr[rows+1], int32 col[nnz], float32 val[nnz].
+
+    Replaces the 5-tuple (row i64, col i64, val f32, d0, d1) of tensorrec/input_utils.py:15-40 and the
+    tf.SparseTensor built from it (tensorrec/tensorrec.py:285-293).  Entry order inside a row is the order the
+    reference's COO conversion yields (stable row sort), duplicates are kept, values are cast to float32."""
+
+    def __init__(self, indptr, col, val, shape):
+        self.indptr, self.col, self.val = indptr, col, val
+        self.shape = (int(shape[0]), int(shape[1]))
+
+    @property
+    def nnz(self):
+        return int(self.col.numel())
+
+    @staticmethod
+    def host_arrays(matrix):
+        """scipy sparse matrix -> (indptr i32, col i32, val f32) numpy arrays, reference entry order."""
+        if not sp.issparse(matrix):
+            raise ValueError('Input must be a scipy sparse matrix')
+        if matrix.shape[0] >= 2 ** 31 - 1 or matrix.shape[1] >= 2 ** 31 - 1 or matrix.nnz >= 2 ** 31 - 1:
+            raise ValueError('feature matrix exceeds int32 indexing')
+        if isinstance(matrix, sp.csr_matrix):
+            # sp.coo_matrix(csr) walks the rows in storage order: the CSR arrays already are that order
+            return (np.ascontiguousarray(matrix.indptr, dtype=np.int32),
+                    np.ascontiguousarray(matrix.indices, dtype=np.int32),
+                    np.ascontiguousarray(matrix.data, dtype=np.float32))
+        coo = matrix if isinstance(matrix, sp.coo_matrix) else sp.coo_matrix(matrix)     # input_utils.py:29-30
+        order = np.argsort(coo.row, kind='stable')
+        counts = np.bincount(coo.row, minlength=coo.shape[0])
+        indptr = np.zeros(coo.shape[0] + 1, dtype=np.int64)
+        np.cumsum(counts, out=indptr[1:])
+        return (indptr.astype(np.int32), np.ascontiguousarray(coo.col[order], dtype=np.int32),
+                np.ascontiguousarray(coo.data[order], dtype=np.float32))
+
+    @classmethod
+    def from_scipy(cls, matrix, device='cuda', pin=False):
+        require_cuda()
+        indptr, col, val = cls.host_arrays(matrix)
+
+        def up(a):
+            t = torch.from_numpy(a)
+            if pin:
+                t = t.pin_memory()
+            return t.to(device, non_blocking=True)
+
+        return cls(up(indptr), up(col), up(val), matrix.shape)
+
+    def h2d_bytes(self):
+        return 4 * (self.indptr.numel() + self.col.numel() + self.val.numel())
+
+
+def gather_reduce(csr, weights, n_normalize=0, want_f32=True, split_d_pad=None):
+    """K1.  Returns (repr_f32 or None, split or None, scale or None)."""
+    lib = require_cuda()
+    rows, n_features = csr.shape
+    d = int(weights.shape[1])
+    if int(weights.shape[0]) != n_features:
+        raise ValueError('feature matrix has %d columns but the weights have %d rows' % (n_features, weights.shape[0]))
+    dev = weights.device
+    out = torch.empty((rows, d), dtype=torch.float32, device=dev) if want_f32 else None
+    split = scale = None
+    d_pad = 0
+    if split_d_pad is not None:
+        d_pad = int(split_d_pad)
+        split = torch.empty((rows, 2 * d_pad), dtype=torch.float16, device=dev)
+        scale = torch.empty((rows,), dtype=torch.float32, device=dev)
+    rc = lib.trk_csr_gather_reduce_f32(_p(csr.indptr), _p(csr.col), _p(csr.val), _p(weights), rows, n_features, d,
+                                       int(n_normalize), _p(out), _p(split), d_pad, _p(scale), _stream())
+    _lib.check(rc, 'trk_csr_gather_reduce_f32')
+    return out, split, scale
+
+
+def split_f32(repr_f32, n_normalize=0, d_pad=None):
+    lib = require_cuda()
+    rows, d = repr_f32.shape
+    d_pad = d_pad_for(d) if d_pad is None else int(d_pad)
+    split = torch.empty((rows, 2 * d_pad), dtype=torch.float16, device=repr_f32.device)
+    scale = torch.empty((rows,), dtype=torch.float32, device=repr_f32.device)
+    rc = lib.trk_split_f32_to_f16x2(_p(repr_f32), rows, d, int(n_normalize), _p(split), d_pad, _p(scale), _stream())
+    _lib.check(rc, 'trk_split_f32_to_f16x2')
+    return split, scale
+
+
+def l2_normalize_rows_(x):
+    lib = require_cuda()
+    rc = lib.trk_l2_normalize_rows_f32(_p(x), x.shape[0], x.shape[1], _stream())
+    _lib.check(rc, 'trk_l2_normalize_rows_f32')
+    return x
+
+
+def project_biases(csr, feature_biases):
+    lib = require_cuda()
+    if int(feature_biases.numel()) != csr.shape[1]:
+        raise ValueError('feature matrix has %d columns but there are %d feature biases'
+                         % (csr.shape[1], feature_biases.numel()))
+    out = torch.empty((csr.shape[0],), dtype=torch.float32, device=feature_biases.device)
+    rc = lib.trk_csr_project_biases_f32(_p(csr.indptr), _p(csr.col), _p(csr.val), _p(feature_biases), csr.shape[0],
+                                        _p(out), _stream())
+    _lib.check(rc, 'trk_csr_project_biases_f32')
+    return out
+
+
+def score_exact(user_repr, item_repr, user_bias=None, item_bias=None, mode=0, attention_repr=None, out=None):
+    """K2 on CUDA cores (exact fp32).  user_repr [T, U, d] or [U, d]; returns [U, I] float32."""
+    lib = require_cuda()
+    if user_repr.dim() == 2:
+        user_repr = user_repr.unsqueeze(0)
+    user_repr = user_repr.contiguous()
+    n_tastes, n_users, d = user_repr.shape
+    n_items = item_repr.shape[0]
+    if item_repr.shape[1] != d:
+        raise ValueError('user and item representations differ in n_components (%d vs %d)' % (d, item_repr.shape[1]))
+    if out is None:
+        out = torch.empty((n_users, n_items), dtype=torch.float32, device=user_repr.device)
+    # grid.y carries 64-row user tiles (<= 65535 per launch): block the user axis for very tall inputs
+    max_rows = 65535 * 64
+    for u0 in range(0, max(n_users, 1), max_rows):
+        u1 = min(n_users, u0 + max_rows)
+        ur = user_repr[:, u0:u1].contiguous() if (u0 > 0 or u1 < n_users) else user_repr
+        ub = None if user_bias is None else user_bias[u0:u1]
+        if attention_repr is not None:
+            ar = attention_repr[:, u0:u1].contiguous()
+            rc = lib.trk_score_attention_f32(_p(ur), _p(ar), _p(item_repr), _p(ub), _p(item_bias), _p(out[u0:u1]),
+                                             u1 - u0, n_items, d, n_tastes, _stream())
+            _lib.check(rc, 'trk_score_attention_f32')
+        else:
+            rc = lib.trk_score_f32(_p(ur), _p(item_repr), _p(ub), _p(item_bias), _p(out[u0:u1]), u1 - u0, n_items, d,
+                                   n_tastes, int(mode), _stream())
+            _lib.check(rc, 'trk_score_f32')
+    return out
+
+
+def rank_full(scores):
+    """K3 (full): the reference's rank_predictions on a dense [U, I] float32 matrix -> int32 ranks."""
+    lib = require_cuda()
+    scores = scores.contiguous()
+    n_users, n_items = scores.shape
+    ranks = torch.empty((n_users, n_items), dtype=torch.int32, device=scores.device)
+    need = int(lib.trk_rank_full_workspace_bytes(n_users, n_items))
+    ws = torch.empty((max(need, 8) // 8,), dtype=torch.int64, device=scores.device) if need else None
+    rc = lib.trk_rank_full(_p(scores), _p(ranks), n_users, n_items, _p(ws), need, _stream())
+    _lib.check(rc, 'trk_rank_full')
+    return ranks
+
+
+def padded_items(n_items):
+    return ((int(n_items) + TILE_ITEMS - 1) // TILE_ITEMS) * TILE_ITEMS
+
+
+def pack_item_meta(item_scale, item_bias, n_items):
+    lib = require_cuda()
+    n_pad = padded_items(n_items)
+    meta = torch.empty((n_pad, 2), dtype=torch.float32, device=item_scale.device)
+    rc = lib.trk_pack_item_meta(_p(item_scale), _p(item_bias), n_items, _p(meta), n_pad, _stream())
+    _lib.check(rc, 'trk_pack_item_meta')
+    return meta
+
+
+def topk_max_k(d_pad):
+    return int(require_cuda().trk_score_topk_max_k(int(d_pad)))
+
+
+def default_splits(n_users, n_items):
+    """Item-range splits so that (user blocks x splits) covers every SM about twice when there are few users."""
+    n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    n_ub = (n_users + TILE_USERS - 1) // TILE_USERS
+    n_tiles = (n_items + TILE_ITEMS - 1) // TILE_ITEMS
+    if n_ub >= n_sm:
+        return 1
+    return int(max(1, min(n_tiles, 256, (2 * n_sm + n_ub - 1) // n_ub)))
+
+
+def score_topk(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, k, n_splits=None,
+               item_id_offset=0):
+    """K2+K3 fused.  Returns (cand_score [U, n_splits, k] f32, cand_item [U, n_splits, k] i32)."""
+    lib = require_cuda()
+    if n_splits is None:
+        n_splits = default_splits(n_users, n_items)
+    dev = user_split.device
+    cand_score = torch.empty((n_users, n_splits, k), dtype=torch.float32, device=dev)
+    cand_item = torch.empty((n_users, n_splits, k), dtype=torch.int32, device=dev)
+    rc = lib.trk_score_topk_f16x3(_p(user_split), _p(user_scale), _p(user_bias), _p(item_split), _p(item_meta),
+                                  n_users, n_items, int(d_pad), int(k), int(n_splits), int(item_id_offset),
+                                  _p(cand_score), _p(cand_item), _stream())
+    _lib.check(rc, 'trk_score_topk_f16x3')
+    return cand_score, cand_item
+
+
+def score_dense_tc(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, out=None):
+    lib = require_cuda()
+    if out is None:
+        out = torch.empty((n_users, n_items), dtype=torch.float32, device=user_split.device)
+    rc = lib.trk_score_dense_f16x3(_p(user_split), _p(user_scale), _p(user_bias), _p(item_split), _p(item_meta),
+                                   n_users, n_items, int(d_pad), _p(out), out.stride(0), _stream())
+    _lib.check(rc, 'trk_score_dense_f16x3')
+    return out
+
+
+def topk_merge(cand_score, cand_item, k_out):
+    """[U, L, k_in] candidate lists -> ([U, k_out] scores, [U, k_out] item ids)."""
+    lib = require_cuda()
+    n_users, n_lists, k_in = cand_score.shape
+    out_s = torch.empty((n_users, k_out), dtype=torch.float32, device=cand_score.device)
+    out_i = torch.empty((n_users, k_out), dtype=torch.int32, device=cand_score.device)
+    rc = lib.trk_topk_merge(_p(cand_score.contiguous()), _p(cand_item.contiguous()), n_users, n_lists, k_in,
+                            int(k_out), _p(out_s), _p(out_i), _stream())
+    _lib.check(rc, 'trk_topk_merge')
+    return out_s, out_i

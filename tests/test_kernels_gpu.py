@@ -1,0 +1,337 @@
+"""GPU parity tests of every C-ABI kernel against the oracle (run on the B200 box: pytest -m gpu).
+
+Bars (BASELINE.json north_star): integer / index results bit-exact; fp32 scores within 1e-5 relative to |u|.|i|."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_known_answers.json')))
+F32 = np.float32
+
+
+@pytest.fixture(scope='module')
+def K():
+    import torch
+    from tensorrec_b200 import kernels
+    kernels.require_cuda()
+    torch.cuda.set_device(0)
+    return kernels
+
+
+def dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def split_to_f32(split, scale, d):
+    s = split.float().cpu().numpy().astype(np.float64)
+    d_pad = s.shape[1] // 2
+    return ((s[:, :d] + s[:, d_pad:d_pad + d]) * scale.cpu().numpy().astype(np.float64)[:, None])
+
+
+# ------------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize('rows,n_features,d,kind', [
+    (100, 200, 100, 'tag'), (150, 200, 128, 'tag'), (1000, 200, 64, 'tag'), (257, 200, 10, 'tag'),
+    (64, 200, 1, 'tag'), (3000, None, 128, 'indicator'), (513, None, 32, 'indicator'), (300, 50, 256, 'tag'),
+    (37, 23, 12, 'messy'), (90, 40, 7, 'messy'), (70, 31, 128, 'messy'),
+])
+@pytest.mark.parametrize('n_norm', [0, 1])
+def test_gather_reduce_matches_oracle(K, rows, n_features, d, kind, n_norm):
+    if kind == 'tag':
+        m = H.tag_features(rows, n_features, min(20, n_features // 2), seed=rows)
+    elif kind == 'indicator':
+        m = H.indicator_features(rows, seed=rows)
+        n_features = m.shape[1]
+    else:
+        m = H.messy_coo(rows, n_features, 6 * rows, seed=rows)
+    w = H.linear_weights(n_features, d, seed=d)
+    coo = oracle.coo_from_sparse(m)
+    expect = oracle.sparse_dense_matmul(coo, w)
+    for _ in range(n_norm):
+        expect = oracle.l2_normalize(expect)
+    csr = K.DeviceCSR.from_scipy(m)
+    d_pad = K.d_pad_for(d)
+    out, split, scale = K.gather_reduce(csr, dev(w), n_normalize=n_norm, want_f32=True, split_d_pad=d_pad)
+    got = out.cpu().numpy()
+    # fp32 accumulation in the same order; FMA contraction and the reduction tree of the norm differ by ulps
+    scale_ref = np.maximum(np.abs(expect).max(axis=1, keepdims=True), 1e-30)
+    assert np.all(np.abs(got - expect) <= 4e-6 * scale_ref + 1e-30)
+    # split operand reproduces the fp32 row to ~2^-21 of the row maximum; the scale is an exact power of two
+    rec = split_to_f32(split, scale, d)
+    assert np.all(np.abs(rec - got) <= 2.0 ** -20 * np.abs(got).max(axis=1, keepdims=True) + 1e-37)
+    sc = scale.cpu().numpy()
+    assert np.all(np.log2(sc) == np.round(np.log2(sc)))
+    pad = split.float().cpu().numpy()
+    assert np.all(pad[:, d:d_pad] == 0) and np.all(pad[:, d_pad + d:] == 0)
+
+
+def test_gather_reduce_integer_exact_and_deterministic(K):
+    m = H.tag_features(500, 200, 20, seed=1, integer=True)
+    w = H.linear_weights(200, 64, seed=2, integer=True)
+    expect = oracle.sparse_dense_matmul(oracle.coo_from_sparse(m), w)
+    csr = K.DeviceCSR.from_scipy(m)
+    a, sa, sca = K.gather_reduce(csr, dev(w), split_d_pad=64)
+    b, sb, scb = K.gather_reduce(csr, dev(w), split_d_pad=64)
+    assert np.array_equal(a.cpu().numpy(), expect)
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())                     # test/test_tensorrec.py:418-458
+    assert np.array_equal(sa.cpu().numpy().view(np.uint16), sb.cpu().numpy().view(np.uint16))
+    assert np.array_equal(split_to_f32(sa, sca, 64), expect.astype(np.float64))  # integers survive the split exactly
+
+
+def test_gather_reduce_input_formats_keep_reference_order(K):
+    # csc / lil / coo inputs must accumulate in the order sp.coo_matrix(...) gives the reference
+    m = H.messy_coo(50, 30, 400, seed=3)
+    w = H.linear_weights(30, 16, seed=4)
+    for conv in (lambda x: x, sp.csc_matrix, sp.csr_matrix, sp.lil_matrix):
+        mm = conv(m)
+        expect = oracle.sparse_dense_matmul(oracle.coo_from_sparse(mm), w)
+        out, _, _ = K.gather_reduce(K.DeviceCSR.from_scipy(mm), dev(w))
+        assert np.all(np.abs(out.cpu().numpy() - expect) <= 4e-6 * np.abs(expect).max() + 1e-30)
+
+
+def test_project_biases_golden_and_random(K):
+    g = GOLDEN['project_biases']
+    feats = sp.coo_matrix(np.array(g['features'], dtype=F32))
+    out = K.project_biases(K.DeviceCSR.from_scipy(feats), dev(np.array(g['feature_biases'], dtype=F32)))
+    assert np.array_equal(out.cpu().numpy(), np.array(g['expected'], dtype=F32))      # exact, as the reference test
+    m = H.tag_features(1234, 200, 20, seed=9)
+    b = H.feature_biases(200, seed=1)
+    expect = oracle.project_biases(oracle.coo_from_sparse(m), b)
+    got = K.project_biases(K.DeviceCSR.from_scipy(m), dev(b)).cpu().numpy()
+    assert np.all(np.abs(got - expect) <= 1e-6)
+
+
+def test_empty_rows_and_empty_matrix(K):
+    m = sp.csr_matrix((5, 8), dtype=F32)
+    w = H.linear_weights(8, 4)
+    out, split, scale = K.gather_reduce(K.DeviceCSR.from_scipy(m), dev(w), n_normalize=1, split_d_pad=64)
+    assert np.all(out.cpu().numpy() == 0) and np.all(split.float().cpu().numpy() == 0)
+    assert np.all(scale.cpu().numpy() == 1.0)
+    assert np.all(K.project_biases(K.DeviceCSR.from_scipy(m), dev(H.feature_biases(8))).cpu().numpy() == 0)
+
+
+# ------------------------------------------------------------------------------------------------- K2 exact
+def test_score_exact_golden(K):
+    g = GOLDEN['dot_product_dense']
+    got = K.score_exact(dev(np.array(g['user_repr'], dtype=F32)), dev(np.array(g['item_repr'], dtype=F32)))
+    assert np.allclose(got.cpu().numpy(), np.array(g['expected']))
+    g = GOLDEN['cosine_dense']
+    u = K.l2_normalize_rows_(dev(np.array(g['user_repr'], dtype=F32)))
+    i = K.l2_normalize_rows_(dev(np.array(g['item_repr'], dtype=F32)))
+    assert np.allclose(K.score_exact(u, i).cpu().numpy(), np.array(g['expected']), atol=1e-6)
+    g = GOLDEN['euclidean_dense']
+    got = K.score_exact(dev(np.array(g['user_repr'], dtype=F32)), dev(np.array(g['item_repr'], dtype=F32)), mode=1)
+    assert np.allclose(got.cpu().numpy(), -np.sqrt(np.array(g['expected_neg_sqrt_of'])), atol=1e-6)
+    g = GOLDEN['bias_prediction_dense']
+    # bias epilogue alone: a 1-component identity "matmul" reproduces the prediction matrix
+    pred = np.array(g['predictions'], dtype=F32)
+    u = np.eye(3, dtype=F32)
+    got = K.score_exact(dev(u), dev(np.ascontiguousarray(pred.T)), dev(np.array(g['user_biases'], dtype=F32)),
+                        dev(np.array(g['item_biases'], dtype=F32)))
+    assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
+
+
+@pytest.mark.parametrize('U,I,d,T', [(100, 150, 100, 1), (65, 130, 17, 3), (300, 257, 128, 2), (1, 1, 1, 1)])
+def test_score_exact_random(K, U, I, d, T):
+    rng = np.random.default_rng(U + I)
+    u = rng.standard_normal((T, U, d)).astype(F32)
+    i = rng.standard_normal((I, d)).astype(F32)
+    ub = rng.standard_normal(U).astype(F32)
+    ib = rng.standard_normal(I).astype(F32)
+    expect = oracle.bias_prediction_dense(
+        oracle.collapse_mixture_of_tastes([oracle.dot_product_dense(u[t], i) for t in range(T)]), ub, ib)
+    got = K.score_exact(dev(u), dev(i), dev(ub), dev(ib)).cpu().numpy()
+    tol = H.norm_tolerance(u, i).max(axis=0) + 1e-6 * (np.abs(ub)[:, None] + np.abs(ib)[None, :])
+    assert np.all(np.abs(got - expect) <= tol)
+    eu = oracle.collapse_mixture_of_tastes([oracle.euclidean_dense(u[t], i) for t in range(T)])
+    got = K.score_exact(dev(u), dev(i), mode=1).cpu().numpy()
+    assert np.allclose(got, eu, rtol=1e-4, atol=1e-4)
+
+
+def test_score_attention_golden_and_random(K):
+    g = GOLDEN['collapse_mixture_of_tastes_with_attention']
+    # 1 user, 4 items, d = 3 one-hot "tastes": pred[t, 0, i] = predictions[t][i] via identity representations
+    preds = np.array(g['predictions'], dtype=F32)
+    atts = np.array(g['attentions'], dtype=F32)
+    T, I = preds.shape
+    # item repr = columns; user repr for taste t picks row t of preds: use d = T*? -> build d = I with item one-hots
+    item = np.eye(I, dtype=F32)
+    u = preds[:, None, :]          # [T, 1, I]: dot with one-hot item i gives preds[t][i]
+    a = atts[:, None, :]
+    got = K.score_exact(dev(u), dev(item), attention_repr=dev(a)).cpu().numpy()[0]
+    expect = np.array(g['expected'], dtype=F32)
+    assert np.all(np.abs(got - expect) <= 4 * np.spacing(expect))
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal((3, 40, 16)).astype(F32)
+    a = rng.standard_normal((3, 40, 16)).astype(F32)
+    it = rng.standard_normal((70, 16)).astype(F32)
+    expect = oracle.collapse_mixture_of_tastes([oracle.dot_product_dense(u[t], it) for t in range(3)],
+                                               [oracle.dot_product_dense(a[t], it) for t in range(3)])
+    got = K.score_exact(dev(u), dev(it), attention_repr=dev(a)).cpu().numpy()
+    assert np.allclose(got, expect, rtol=2e-5, atol=2e-5)
+
+
+def test_taste_max_golden(K):
+    g = GOLDEN['collapse_mixture_of_tastes']
+    preds = np.array(g['predictions'], dtype=F32)
+    got = K.score_exact(dev(preds[:, None, :]), dev(np.eye(4, dtype=F32))).cpu().numpy()[0]
+    assert np.array_equal(got, np.array(g['expected'], dtype=F32))
+
+
+# ------------------------------------------------------------------------------------------------- K3 full
+def test_rank_full_golden(K):
+    g = GOLDEN['rank_predictions']
+    got = K.rank_full(dev(np.array(g['predictions'], dtype=F32))).cpu().numpy()
+    assert got.dtype == np.int32 and np.array_equal(got, np.array(g['expected']))
+
+
+@pytest.mark.parametrize('U,I', [(3, 1), (7, 2), (100, 150), (33, 1000), (5, 4096), (9, 4097), (6, 9000), (3, 20000)])
+def test_rank_full_matches_double_sort_with_ties(K, U, I):
+    rng = np.random.default_rng(I)
+    s = rng.integers(-4, 5, size=(U, I)).astype(F32)           # heavy ties
+    s[0, ::3] = -0.0                                            # -0.0 ties with +0.0
+    assert np.array_equal(K.rank_full(dev(s)).cpu().numpy(), oracle.rank_predictions(s))
+    f = rng.standard_normal((U, I)).astype(F32)
+    f[:, : I // 2] = f[:, I - I // 2:][:, : I // 2]             # exact float duplicates
+    r = K.rank_full(dev(f)).cpu().numpy()
+    assert np.array_equal(r, oracle.rank_predictions(f))
+    assert r.min() == 1 and r.max() == I                        # test/test_tensorrec.py:204-212: ranks > 0
+
+
+# ------------------------------------------------------------------------------------------------- K2+K3 fused
+def make_case(U, I, d, integer, seed, biased=True, regime='tag'):
+    if regime == 'tag':
+        uf = H.tag_features(U, 200, 20, seed=seed, integer=integer)
+        itf = H.tag_features(I, 200, 20, seed=seed + 1, integer=integer)
+    else:
+        uf = H.indicator_features(U, seed=seed)
+        itf = H.indicator_features(I, seed=seed + 1)
+    wu = H.linear_weights(uf.shape[1], d, seed=seed + 2, integer=integer)
+    wi = H.linear_weights(itf.shape[1], d, seed=seed + 3, integer=integer)
+    bu = H.feature_biases(uf.shape[1], seed=seed + 4, integer=integer) if biased else None
+    bi = H.feature_biases(itf.shape[1], seed=seed + 5, integer=integer) if biased else None
+    return uf, itf, wu, wi, bu, bi
+
+
+def run_fused(K, uf, itf, wu, wi, bu, bi, k, n_splits=None, n_norm=0, offset=0):
+    d = wu.shape[1]
+    d_pad = K.d_pad_for(d)
+    ucsr, icsr = K.DeviceCSR.from_scipy(uf), K.DeviceCSR.from_scipy(itf)
+    _, us, usc = K.gather_reduce(ucsr, dev(wu), n_normalize=n_norm, want_f32=False, split_d_pad=d_pad)
+    _, its, isc = K.gather_reduce(icsr, dev(wi), n_normalize=n_norm, want_f32=False, split_d_pad=d_pad)
+    ub = K.project_biases(ucsr, dev(bu)) if bu is not None else None
+    ib = K.project_biases(icsr, dev(bi)) if bi is not None else None
+    meta = K.pack_item_meta(isc, ib, itf.shape[0])
+    cs, ci = K.score_topk(us, usc, ub, its, meta, uf.shape[0], itf.shape[0], d_pad, k, n_splits=n_splits,
+                          item_id_offset=offset)
+    top_s, top_i = K.topk_merge(cs, ci, k)
+    return top_s.cpu().numpy(), top_i.cpu().numpy(), (us, usc, ub, its, meta, d_pad)
+
+
+def oracle_scores(uf, itf, wu, wi, bu, bi, prediction='dot'):
+    model = oracle.OracleModel([wu], wi, bu, bi, prediction=prediction)
+    return model.predict(uf, itf)
+
+
+@pytest.mark.parametrize('U,I,d,k,splits', [
+    (100, 150, 100, 10, None), (256, 4096, 64, 10, 1), (256, 4096, 64, 10, 5), (130, 1000, 128, 32, 3),
+    (1, 300, 64, 1, 2), (300, 257, 128, 7, None), (129, 513, 10, 10, 4),
+])
+def test_fused_topk_integer_fixture_exact(K, U, I, d, k, splits):
+    """Integer-valued features/weights: every product and partial sum is exact in fp32 and in the split-fp16 MMA,
+    so ids AND scores must equal the reference order bit for bit, with many ties (lower id first)."""
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, True, seed=U + I)
+    scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    got_s, got_i, _ = run_fused(K, uf, itf, wu, wi, bu, bi, k, n_splits=splits)
+    assert np.array_equal(got_i, exp_i)
+    assert np.array_equal(got_s, exp_s)
+
+
+@pytest.mark.parametrize('U,I,d,k,regime,cosine', [
+    (100, 150, 100, 10, 'tag', False), (500, 3000, 128, 10, 'indicator', False), (200, 2000, 64, 20, 'tag', True),
+])
+def test_fused_topk_float_within_tolerance(K, U, I, d, k, regime, cosine):
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=U, regime=regime)
+    model = oracle.OracleModel([wu], wi, bu, bi, prediction='cosine' if cosine else 'dot')
+    scores = model.predict(uf, itf)
+    ur, ir = model.user_representation(uf)[0], model.item_representation(itf)
+    if cosine:
+        ur, ir = oracle.l2_normalize(ur), oracle.l2_normalize(ir)
+    tol = H.norm_tolerance(ur, ir, rel=1e-5) + 1e-6
+    got_s, got_i, _ = run_fused(K, uf, itf, wu, wi, bu, bi, k, n_norm=1 if cosine else 0)
+    rows = np.arange(U)[:, None]
+    # 1) scores of the returned items agree with the oracle within 1e-5 * |u||i|
+    assert np.all(np.abs(got_s - scores[rows, got_i]) <= tol[rows, got_i])
+    # 2) the returned set is a valid top-k: nothing outside it beats the k-th returned score by more than tol
+    kth = got_s[:, -1:]
+    mask = np.ones_like(scores, dtype=bool)
+    mask[rows, got_i] = False
+    assert np.all((scores - tol)[mask.reshape(scores.shape)].reshape(U, -1) <= kth + 1e-6)
+    # 3) ordered by score descending
+    assert np.all(np.diff(got_s, axis=1) <= 0)
+
+
+def test_fused_topk_offset_and_sharded_merge(K):
+    """Item-axis shards (the multi-GPU layout) run one after the other on one GPU: merged result == unsharded."""
+    import torch
+    U, I, d, k = 200, 3000, 64, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, True, seed=7)
+    exp_i, exp_s = oracle.top_k_from_scores(oracle_scores(uf, itf, wu, wi, bu, bi), k)
+    shards = [(0, 1100), (1100, 1900), (1900, 3000)]
+    cs, ci = [], []
+    for lo, hi in shards:
+        s, i, _ = run_fused(K, uf, itf[lo:hi], wu, wi, bu, bi, k, offset=lo)
+        cs.append(torch.from_numpy(s).cuda())
+        ci.append(torch.from_numpy(i).cuda())
+    ms, mi = K.topk_merge(torch.stack(cs, 1), torch.stack(ci, 1), k)
+    assert np.array_equal(mi.cpu().numpy(), exp_i) and np.array_equal(ms.cpu().numpy(), exp_s)
+
+
+def test_fused_topk_k_larger_than_items_pads_with_sentinels(K):
+    uf, itf, wu, wi, bu, bi = make_case(40, 6, 64, True, seed=11)
+    got_s, got_i, _ = run_fused(K, uf, itf, wu, wi, bu, bi, k=10)
+    exp_i, exp_s = oracle.top_k_from_scores(oracle_scores(uf, itf, wu, wi, bu, bi), 6)
+    assert np.array_equal(got_i[:, :6], exp_i) and np.array_equal(got_s[:, :6], exp_s)
+    assert np.all(got_i[:, 6:] == 2 ** 31 - 1) and np.all(np.isneginf(got_s[:, 6:]))
+
+
+def test_dense_tc_matches_exact(K):
+    for (U, I, d, integer) in [(100, 150, 100, True), (300, 1000, 64, False), (129, 257, 128, False)]:
+        uf, itf, wu, wi, bu, bi = make_case(U, I, d, integer, seed=U)
+        scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+        _, _, (us, usc, ub, its, meta, d_pad) = run_fused(K, uf, itf, wu, wi, bu, bi, k=1)
+        got = K.score_dense_tc(us, usc, ub, its, meta, U, I, d_pad).cpu().numpy()
+        if integer:
+            assert np.array_equal(got, scores)
+        else:
+            model = oracle.OracleModel([wu], wi, bu, bi)
+            tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + 1e-6
+            assert np.all(np.abs(got - scores) <= tol)
+
+
+def test_topk_merge_orders_ties_by_lower_id(K):
+    import torch
+    s = torch.tensor([[[5., 3., 1.], [5., 4., 1.], [9., 1., -float('inf')]]], device='cuda')
+    i = torch.tensor([[[7, 1, 30], [2, 9, 11], [40, 10, 2 ** 31 - 1]]], dtype=torch.int32, device='cuda')
+    ms, mi = K.topk_merge(s, i, 6)
+    assert mi.cpu().tolist() == [[40, 2, 7, 9, 1, 10]]
+    assert ms.cpu().tolist() == [[9., 5., 5., 4., 3., 1.]]
+
+
+def test_unsupported_shapes_raise(K):
+    from tensorrec_b200._lib import TrkUnsupportedError
+    uf, itf, wu, wi, bu, bi = make_case(10, 20, 64, True, seed=1)
+    with pytest.raises(TrkUnsupportedError):
+        run_fused(K, uf, itf, wu, wi, bu, bi, k=K.topk_max_k(64) + 1)
