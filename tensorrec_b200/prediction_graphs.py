@@ -1,0 +1,86 @@
+"""Prediction plugin graphs: (user_repr, item_repr) -> scores (API of tensorrec/prediction_graphs.py).
+
+`connect_dense_prediction_graph` / `connect_serial_prediction_graph` keep the reference's names and argument
+meaning (prediction_graphs.py:11-40).  They accept torch tensors (differentiable: this is what the training step
+runs) -- and, for the dense form, CUDA tensors or numpy arrays are scored by the hand-written kernels when no
+gradient is needed (the predict / predict_rank hot path; TensorRec lowers built-in graphs by `b200_kind`)."""
+import numpy as np
+import torch
+
+
+def _l2_normalize(x, eps=1e-12):
+    return x * torch.rsqrt(torch.clamp(torch.sum(x * x, dim=1, keepdim=True), min=eps))
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _as_device_f32(x):
+    """numpy / CPU tensor -> float32 CUDA tensor for the kernel path (raises without a CUDA device)."""
+    from . import kernels
+    kernels.require_cuda()
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    return x.to(device='cuda', dtype=torch.float32).contiguous()
+
+
+class AbstractPredictionGraph(object):
+    b200_kind = None
+
+    def connect_dense_prediction_graph(self, tf_user_representation, tf_item_representation):
+        pass
+
+    def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
+        pass
+
+
+class DotProductPredictionGraph(AbstractPredictionGraph):
+    """prediction = user_repr . item_repr (prediction_graphs.py:43-55)."""
+    b200_kind = 'dot'
+
+    def connect_dense_prediction_graph(self, tf_user_representation, tf_item_representation):
+        if _needs_grad(tf_user_representation, tf_item_representation):
+            return tf_user_representation @ tf_item_representation.t()
+        from . import kernels
+        return kernels.score_exact(_as_device_f32(tf_user_representation), _as_device_f32(tf_item_representation))
+
+    def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
+        gathered_user_reprs = tf_user_representation[tf_x_user]
+        gathered_item_reprs = tf_item_representation[tf_x_item]
+        return torch.sum(gathered_user_reprs * gathered_item_reprs, dim=1)
+
+
+class CosineSimilarityPredictionGraph(AbstractPredictionGraph):
+    """prediction = cos(user_repr, item_repr) (prediction_graphs.py:58-72)."""
+    b200_kind = 'cosine'
+
+    def connect_dense_prediction_graph(self, tf_user_representation, tf_item_representation):
+        from .recommendation_graphs import relative_cosine
+        return relative_cosine(tf_tensor_1=tf_user_representation, tf_tensor_2=tf_item_representation)
+
+    def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
+        normalized_users = _l2_normalize(tf_user_representation)
+        normalized_items = _l2_normalize(tf_item_representation)
+        return torch.sum(normalized_users[tf_x_user] * normalized_items[tf_x_item], dim=1)
+
+
+class EuclideanSimilarityPredictionGraph(AbstractPredictionGraph):
+    """prediction = -sqrt(max(|u|^2 - 2 u.i + |i|^2, 1e-16)) (prediction_graphs.py:75-117)."""
+    b200_kind = 'euclidean'
+    epsilon = 1e-16
+
+    def connect_dense_prediction_graph(self, tf_user_representation, tf_item_representation):
+        if _needs_grad(tf_user_representation, tf_item_representation):
+            r_user = torch.sum(tf_user_representation ** 2, 1, keepdim=True)
+            r_item = torch.sum(tf_item_representation ** 2, 1, keepdim=True)
+            distance = r_user - 2.0 * (tf_user_representation @ tf_item_representation.t()) + r_item.t()
+            return -1.0 * torch.sqrt(torch.clamp(distance, min=self.epsilon))
+        from . import kernels
+        return kernels.score_exact(_as_device_f32(tf_user_representation), _as_device_f32(tf_item_representation),
+                                   mode=1)
+
+    def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
+        delta = (tf_user_representation[tf_x_user] - tf_item_representation[tf_x_item]) ** 2
+        distance = torch.clamp(torch.sum(delta, dim=1), min=self.epsilon)
+        return -1.0 * torch.sqrt(distance)

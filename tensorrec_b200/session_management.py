@@ -1,0 +1,67 @@
+"""Process-wide execution context.
+
+The reference keeps one global tf.Session (tensorrec/session_management.py:3-21); tests reset it with
+set_session(None).  Here the "session" is the CUDA device + stream the kernels are launched on, plus the variable
+scope (name -> parameter tensor) that plugin graphs create their weights in -- the define-by-run analogue of the
+TF graph's variable collection."""
+import contextlib
+import threading
+
+import torch
+
+
+class Session(object):
+    def __init__(self, device=None):
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device('cpu')
+        self.device = torch.device(device)
+
+    @property
+    def is_cuda(self):
+        return self.device.type == 'cuda'
+
+
+_session = None
+
+
+def get_session():
+    global _session
+    if _session is None:
+        _session = Session()
+    return _session
+
+
+def set_session(session):
+    global _session
+    _session = session
+
+
+# ---- variable scope ------------------------------------------------------------------------------------
+_scope = threading.local()
+
+
+@contextlib.contextmanager
+def variable_scope(store):
+    """Makes `store` (an ordered dict name -> tensor) the target of get_variable() inside the block."""
+    previous = getattr(_scope, 'store', None)
+    _scope.store = store
+    try:
+        yield store
+    finally:
+        _scope.store = previous
+
+
+def get_variable(name, initializer):
+    """Returns the trainable tensor registered under `name`, creating it with initializer() on first use.
+
+    Plugin graphs must create their weights through this function: `connect_*` methods run on every training step
+    (define-by-run), and a weight created any other way would be re-initialised each step."""
+    store = getattr(_scope, 'store', None)
+    if store is None:
+        value = initializer()
+        return value.requires_grad_(True) if value.is_floating_point() else value
+    if name not in store:
+        value = initializer().detach().clone()
+        store[name] = value.requires_grad_(True)
+    return store[name]
