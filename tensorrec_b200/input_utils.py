@@ -78,5 +78,5 @@ class SparseInput(object):
             ds = self.dataset
             idx = torch.from_numpy(np.stack([ds.row_index, ds.col_index]))
             self._torch[key] = torch.sparse_coo_tensor(idx, torch.from_numpy(ds.values), size=self.shape,
-                                                       is_coalesced=False).to(device)
+                                                       is_coalesced=False, check_invariants=False).to(device)
         return self._torch[key]

@@ -13,7 +13,12 @@ def _l2_normalize(x, eps=1e-12):
 
 
 def _needs_grad(*tensors):
-    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+    """True -> some input carries a gradient: differentiable torch ops (training step); False -> kernels on CUDA."""
+    for t in tensors:
+        if isinstance(t, torch.Tensor):
+            if t.requires_grad and torch.is_grad_enabled():
+                return True
+    return False
 
 
 def _as_device_f32(x):

@@ -13,7 +13,13 @@ from .session_management import get_variable
 
 
 def _needs_grad(*tensors):
-    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+    """True -> some input carries a gradient: evaluate with differentiable torch ops (the training step).
+    False -> plain arrays / gradient-free tensors: evaluate with the kernels on the CUDA device (no CPU path)."""
+    for t in tensors:
+        if isinstance(t, torch.Tensor):
+            if t.requires_grad and torch.is_grad_enabled():
+                return True
+    return False
 
 
 def _dev(x, dtype=torch.float32):

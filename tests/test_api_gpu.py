@@ -1,0 +1,292 @@
+"""GPU tests of the drop-in boundary: the TensorRec class driving the kernels through the C ABI, checked against the
+oracle with injected weights (the reference never seeds its initialiser, so values after fit() are unpinned) and
+against the contract tests of the reference's test/test_tensorrec.py, test_readme.py (cited per test)."""
+import logging
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope='module')
+def T():
+    import torch
+    import tensorrec_b200
+    from tensorrec_b200 import kernels
+    kernels.require_cuda()
+    torch.cuda.set_device(0)
+    return tensorrec_b200
+
+
+def build(T, uf, itf, d, n_tastes=1, user_repr='linear', item_repr='linear', prediction='dot', biased=True,
+          attention=False, integer=False, seed=0):
+    """A TensorRec with injected weights and the OracleModel holding the same weights."""
+    R, P = T.representation_graphs, T.prediction_graphs
+    reprs = {'linear': R.LinearRepresentationGraph, 'normalized_linear': R.NormalizedLinearRepresentationGraph}
+    preds = {'dot': P.DotProductPredictionGraph, 'cosine': P.CosineSimilarityPredictionGraph,
+             'euclidean': P.EuclideanSimilarityPredictionGraph}
+    model = T.TensorRec(n_components=d, n_tastes=n_tastes, user_repr_graph=reprs[user_repr](),
+                        item_repr_graph=reprs[item_repr](), prediction_graph=preds[prediction](), biased=biased,
+                        attention_graph=R.LinearRepresentationGraph() if attention else None)
+    fu, fi = uf.shape[1], itf.shape[1]
+    wu = [H.linear_weights(fu, d, seed=seed + 10 + t, integer=integer) for t in range(n_tastes)]
+    wi = H.linear_weights(fi, d, seed=seed + 3, integer=integer)
+    wa = [H.linear_weights(fu, d, seed=seed + 20 + t, integer=integer) for t in range(n_tastes)] if attention else None
+    bu = H.feature_biases(fu, seed=seed + 4, integer=integer) if biased else None
+    bi = H.feature_biases(fi, seed=seed + 5, integer=integer) if biased else None
+    weights = {'linear_weights_item': wi}
+    for t in range(n_tastes):
+        weights['linear_weights_user_%d' % t] = wu[t]
+        if attention:
+            weights['linear_weights_attn_%d' % t] = wa[t]
+    if biased:
+        weights['feature_biases_user'] = bu.reshape(-1, 1)
+        weights['feature_biases_item'] = bi.reshape(-1, 1)
+    model.set_weights(weights)
+    om = oracle.OracleModel(wu, wi, bu, bi, attention_weights=wa, user_repr=user_repr, item_repr=item_repr,
+                            prediction=prediction)
+    return model, om
+
+
+def score_tolerance(om, uf, itf, rel=1e-5):
+    ur = om.user_representation(uf)
+    ir = om.item_representation(itf)
+    if om.prediction == 'cosine':
+        ur = np.stack([oracle.l2_normalize(u) for u in ur])
+        ir = oracle.l2_normalize(ir)
+    return H.norm_tolerance(ur, ir, rel).max(axis=0) + 2e-6
+
+
+# ---- BASELINE config #1: the README flow (test/test_readme.py:6-31) --------------------------------------------
+def test_readme_flow_fit_predict_rank_recall(T, caplog):
+    model = T.TensorRec()
+    interactions, user_features, item_features = T.util.generate_dummy_data(num_users=100, num_items=150,
+                                                                            interaction_density=.05, seed=0)
+    with caplog.at_level(logging.INFO):
+        model.fit(interactions, user_features, item_features, epochs=5, verbose=True)
+    assert any('EPOCH 4 BATCH 0 loss' in r.getMessage() for r in caplog.records)
+    predictions = model.predict(user_features=user_features, item_features=item_features)
+    predicted_ranks = model.predict_rank(user_features=user_features, item_features=item_features)
+    assert predictions.shape == (100, 150) and predictions.dtype == np.float32
+    assert predicted_ranks.shape == (100, 150) and predicted_ranks.dtype == np.int32
+    assert (predicted_ranks > 0).all()                                           # test/test_tensorrec.py:204-212
+    assert np.array_equal(np.sort(predicted_ranks, axis=1), np.tile(np.arange(1, 151), (100, 1)))
+    # ranks are exactly the reference ranking of the returned scores
+    assert np.array_equal(predicted_ranks, oracle.rank_predictions(predictions))
+    r_at_k = T.eval.recall_at_k(predicted_ranks, interactions, k=10)
+    assert 0.0 <= np.mean(r_at_k) <= 1.0
+    # the whole fitted model agrees with the oracle evaluated on the fitted weights
+    w = model.get_weights()
+    om = oracle.OracleModel([w['linear_weights_user_0']], w['linear_weights_item'], w['feature_biases_user'][:, 0],
+                            w['feature_biases_item'][:, 0])
+    assert np.all(np.abs(predictions - om.predict(user_features, item_features))
+                  <= score_tolerance(om, user_features, item_features))
+
+
+# ---- end-to-end parity with injected weights ---------------------------------------------------------------------
+@pytest.mark.parametrize('path', ['auto', 'exact'])
+@pytest.mark.parametrize('prediction,user_repr', [('dot', 'linear'), ('cosine', 'linear'), ('dot', 'normalized_linear'),
+                                                  ('cosine', 'normalized_linear')])
+def test_predict_matches_oracle_float(T, monkeypatch, path, prediction, user_repr):
+    monkeypatch.setattr(T.tensorrec, 'SCORE_PATH', path)
+    uf, itf = H.tag_features(100, 200, 20, seed=1), H.tag_features(150, 200, 20, seed=2)
+    model, om = build(T, uf, itf, d=100, user_repr=user_repr, prediction=prediction)
+    got = model.predict(uf, itf)
+    expect = om.predict(uf, itf)
+    assert got.shape == (100, 150) and got.dtype == np.float32
+    assert np.all(np.abs(got - expect) <= score_tolerance(om, uf, itf))
+    # ranks: exact w.r.t. the kernel's own scores; vs the oracle they may differ only inside the score tolerance
+    ranks = model.predict_rank(uf, itf)
+    assert np.array_equal(ranks, oracle.rank_predictions(got))
+    expect_ranks = om.predict_rank(uf, itf)
+    differing = ranks != expect_ranks
+    assert differing.mean() < 0.01
+
+
+@pytest.mark.parametrize('path', ['auto', 'exact'])
+@pytest.mark.parametrize('U,I,d', [(100, 150, 100), (256, 4096, 64), (77, 5000, 128), (50, 300, 10)])
+def test_predict_and_rank_exact_on_integer_fixture(T, monkeypatch, path, U, I, d):
+    """SURVEY 8d parity fixture: features in {0,1}, weights in {-2..2}, integer biases -> scores are exact in every
+    arithmetic path, ties are everywhere, and the full int32 rank matrix must equal the reference's double sort."""
+    monkeypatch.setattr(T.tensorrec, 'SCORE_PATH', path)
+    uf = H.tag_features(U, 200, 20, seed=U, integer=True)
+    itf = H.tag_features(I, 200, 20, seed=I, integer=True)
+    model, om = build(T, uf, itf, d=d, integer=True)
+    scores = om.predict(uf, itf)
+    assert np.array_equal(model.predict(uf, itf), scores)
+    assert np.array_equal(model.predict_rank(uf, itf), oracle.rank_predictions(scores))
+    top = model.predict_rank(uf, itf, k=10)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, 10)
+    assert np.array_equal(top.items, exp_i) and np.array_equal(top.scores, exp_s)
+
+
+def test_tastes_normalized_cosine_and_attention(T):
+    # test/test_tensorrec.py:278-339 shapes; values against the oracle
+    uf, itf = H.tag_features(15, 200, 20, seed=1), H.tag_features(30, 200, 20, seed=2)
+    model, om = build(T, uf, itf, d=10, n_tastes=3, user_repr='normalized_linear', prediction='cosine')
+    got = model.predict(uf, itf)
+    assert np.all(np.abs(got - om.predict(uf, itf)) <= 3e-6)
+    assert model.predict_user_representation(uf).shape == (3, 15, 10)
+    assert np.array_equal(model.predict_rank(uf, itf), oracle.rank_predictions(got))
+    top = model.predict_rank(uf, itf, k=5)                       # n_tastes > 1: the non-fused top-k route
+    exp_i, exp_s = oracle.top_k_from_scores(got, 5)
+    assert np.array_equal(top.items, exp_i) and np.array_equal(top.scores, exp_s)
+
+    model, om = build(T, uf, itf, d=10, n_tastes=3, attention=True)
+    got = model.predict(uf, itf)
+    expect = om.predict(uf, itf)
+    assert np.allclose(got, expect, rtol=2e-5, atol=2e-5)
+    assert model.predict_user_attention_representation(uf).shape == (3, 15, 10)
+
+    model, om = build(T, uf, itf, d=10, prediction='euclidean', n_tastes=2)
+    assert np.allclose(model.predict(uf, itf), om.predict(uf, itf), rtol=1e-4, atol=1e-4)
+
+
+def test_representations_and_biases(T):
+    # test/test_tensorrec.py:226-275
+    uf, itf = H.tag_features(15, 200, 20, seed=1), H.tag_features(30, 200, 20, seed=2)
+    model, om = build(T, uf, itf, d=10)
+    ur, ir = model.predict_user_representation(uf), model.predict_item_representation(itf)
+    assert ur.shape == (15, 10) and ir.shape == (30, 10)
+    assert np.allclose(ur, om.user_representation(uf)[0], atol=1e-6)
+    assert np.allclose(ir, om.item_representation(itf), atol=1e-6)
+    ub, ib = model.predict_user_bias(uf), model.predict_item_bias(itf)
+    assert ub.shape == (15,) and ib.shape == (30,) and np.any(ub != 0) and np.any(ib != 0)
+    assert np.allclose(ub, oracle.project_biases(oracle.coo_from_sparse(uf), om.user_bias), atol=1e-6)
+    unbiased, _ = build(T, uf, itf, d=10, biased=False)
+    with pytest.raises(T.errors.ModelNotBiasedException):
+        unbiased.predict_user_bias(uf)
+    assert unbiased.predict(uf, itf).shape == (15, 30)
+
+
+def test_predict_similar_items(T):
+    itf = H.tag_features(30, 200, 20, seed=2)
+    uf = H.tag_features(15, 200, 20, seed=1)
+    model, om = build(T, uf, itf, d=10, prediction='cosine')
+    sims = model.predict_similar_items(itf, item_ids=[6, 12], n_similar=5)
+    assert len(sims) == 2 and all(len(s) == 5 for s in sims)
+    expect = oracle.predict_similar_items('cosine', om.item_representation(itf), [6, 12])
+    for row, ids in zip(sims, [6, 12]):
+        assert row[0][0] == ids and abs(row[0][1] - 1.0) < 1e-5          # an item is most similar to itself
+        for item_id, score in row:
+            assert abs(score - expect[[6, 12].index(ids), item_id]) < 1e-5
+
+
+# ---- determinism and persistence (test/test_tensorrec.py:418-458) -----------------------------------------------
+def test_repeat_and_reload_are_bit_identical(T):
+    interactions, uf, itf = T.util.generate_dummy_data(num_users=15, num_items=30, interaction_density=.5, seed=3)
+    model = T.TensorRec(n_components=10)
+    model.fit(interactions, uf, itf, epochs=5)
+    predictions, ranks = model.predict(uf, itf), model.predict_rank(uf, itf)
+    top = model.predict_rank(uf, itf, k=7)
+    with tempfile.TemporaryDirectory() as tmp:
+        model.save_model(os.path.join(tmp, 'm'))
+        assert np.array_equal(predictions, model.predict(uf, itf))
+        assert np.array_equal(ranks, model.predict_rank(uf, itf))
+        T.session_management.set_session(None)
+        new_model = T.TensorRec.load_model(os.path.join(tmp, 'm'))
+    assert np.array_equal(predictions, new_model.predict(uf, itf))
+    assert np.array_equal(ranks, new_model.predict_rank(uf, itf))
+    again = new_model.predict_rank(uf, itf, k=7)
+    assert np.array_equal(top.items, again.items) and np.array_equal(top.scores, again.scores)
+
+
+# ---- the plugin surface: a user-defined representation graph (test/test_readme.py:33-68) --------------------------
+def test_custom_representation_graph_runs_through_the_kernels(T):
+    import torch
+
+    class TanhRepresentationGraph(T.representation_graphs.AbstractRepresentationGraph):
+        def connect_representation_graph(self, tf_features, n_components, n_features, node_name_ending):
+            tf_tanh_weights = T.session_management.get_variable(
+                'tanh_weights_%s' % node_name_ending,
+                lambda: torch.randn(n_features, n_components, device=tf_features.device) * .5)
+            tf_repr = torch.tanh(torch.sparse.mm(tf_features, tf_tanh_weights))
+            return tf_repr, [tf_tanh_weights]
+
+    interactions, uf, itf = T.util.generate_dummy_data(num_users=100, num_items=150, interaction_density=.05, seed=1)
+    model = T.TensorRec(n_components=10, user_repr_graph=TanhRepresentationGraph(),
+                        item_repr_graph=T.representation_graphs.NormalizedLinearRepresentationGraph())
+    model.fit(interactions, uf, itf, epochs=5)
+    w = model.get_weights()
+    ur = np.tanh(oracle.sparse_dense_matmul(oracle.coo_from_sparse(uf), w['tanh_weights_user_0']))
+    ir = oracle.normalized_linear_representation(oracle.coo_from_sparse(itf), w['linear_weights_item'])
+    expect = oracle.bias_prediction_dense(
+        oracle.dot_product_dense(ur, ir), oracle.project_biases(oracle.coo_from_sparse(uf), w['feature_biases_user']),
+        oracle.project_biases(oracle.coo_from_sparse(itf), w['feature_biases_item']))
+    got = model.predict(uf, itf)
+    assert np.all(np.abs(got - expect) <= H.norm_tolerance(ur, ir, 2e-5) + 1e-5)
+    assert np.array_equal(model.predict_rank(uf, itf), oracle.rank_predictions(got))
+    top = model.predict_rank(uf, itf, k=10)
+    assert np.array_equal(top.items, oracle.top_k_from_scores(got, 10)[0])
+
+
+# ---- BASELINE config #3: MovieLens-1M-shaped, cosine, recall@10 ----------------------------------------------------
+def test_movielens_shaped_cosine_full_rank_and_topk_agree(T):
+    n_users, n_items = 6040, 3706
+    rng = np.random.default_rng(0)
+    uf = sp.identity(n_users, format='csr', dtype=F32)
+    genres = sp.random(n_items, 18, density=1.65 / 18, format='csr', random_state=rng, dtype=np.float64)
+    genres.data[:] = 1.0
+    itf = sp.hstack([sp.identity(n_items, format='csr', dtype=F32), genres.astype(F32)]).tocsr()
+    model, om = build(T, uf, itf, d=128, prediction='cosine', biased=True)
+    n_int = 200000
+    interactions = sp.csr_matrix((np.ones(n_int, dtype=F32), (rng.integers(0, n_users, n_int),
+                                                              rng.integers(0, n_items, n_int))), shape=(n_users, n_items))
+    ranks = model.predict_rank(uf, itf)
+    assert ranks.shape == (n_users, n_items) and ranks.dtype == np.int32
+    scores = model.predict(uf, itf)
+    sample = rng.choice(n_users, 64, replace=False)
+    assert np.array_equal(ranks[sample], oracle.rank_predictions(scores[sample]))
+    expect = om.predict(uf[sample], itf)
+    assert np.all(np.abs(scores[sample] - expect) <= score_tolerance(om, uf[sample], itf))
+    top = model.predict_rank(uf, itf, k=10)
+    full_recall = T.eval.recall_at_k(ranks, interactions, k=10)
+    topk_recall = T.eval.recall_at_k(top, interactions, k=10)
+    assert np.allclose(full_recall, topk_recall)
+    # the fused kernel's ids are the rank <= 10 entries of the full-rank route
+    rows = np.arange(n_users)[:, None]
+    assert np.array_equal(ranks[rows, top.items], np.tile(np.arange(1, 11), (n_users, 1)))
+
+
+def test_recommendation_graph_functions_evaluate_on_the_device(T):
+    """The functional surface of tensorrec/recommendation_graphs.py with the reference's own known answers
+    (test/test_recommendation_graphs.py), numpy in -> kernels -> device tensor out."""
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_known_answers.json')))
+    RG, PG = T.recommendation_graphs, T.prediction_graphs
+    g = G['rank_predictions']
+    assert np.array_equal(RG.rank_predictions(np.array(g['predictions'], dtype=F32)).cpu().numpy(), g['expected'])
+    g = G['project_biases']
+    got = RG.project_biases_with(sp.coo_matrix(np.array(g['features'], dtype=F32)), g['feature_biases'])
+    assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
+    g = G['bias_prediction_dense']
+    got = RG.bias_prediction_dense(np.array(g['predictions'], dtype=F32), np.array(g['user_biases'], dtype=F32),
+                                   np.array(g['item_biases'], dtype=F32))
+    assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
+    g = G['collapse_mixture_of_tastes']
+    got = RG.collapse_mixture_of_tastes([np.array(p, dtype=F32) for p in g['predictions']], None)
+    assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
+    g = G['collapse_mixture_of_tastes_with_attention']
+    got = RG.collapse_mixture_of_tastes([np.array(p, dtype=F32) for p in g['predictions']],
+                                        [np.array(a, dtype=F32) for a in g['attentions']]).cpu().numpy()
+    assert np.all(np.abs(got - np.array(g['expected'], dtype=F32)) <= 4 * np.spacing(np.array(g['expected'], dtype=F32)))
+    g = G['dot_product_dense']
+    got = PG.DotProductPredictionGraph().connect_dense_prediction_graph(
+        tf_user_representation=np.array(g['user_repr']), tf_item_representation=np.array(g['item_repr']))
+    assert np.allclose(got.cpu().numpy(), g['expected'])
+    g = G['cosine_dense']
+    got = PG.CosineSimilarityPredictionGraph().connect_dense_prediction_graph(
+        tf_user_representation=np.array(g['user_repr']), tf_item_representation=np.array(g['item_repr']))
+    assert np.allclose(got.cpu().numpy(), g['expected'], atol=1e-6)
+    g = G['predict_similar_items_cosine']
+    got = RG.predict_similar_items(PG.CosineSimilarityPredictionGraph(), np.array(g['item_repr'], dtype=F32),
+                                   g['item_ids'])
+    assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
