@@ -76,9 +76,10 @@ __host__ __device__ inline SmemLayout make_layout(int n_kblocks, int n_stages, i
 // barrier block (uint64 each): [0] a_full, [1] a_empty, [2..3] tmem_full, [4..5] tmem_empty,
 // [6 .. 6+S) b_full, [6+S .. 6+2S) b_empty; then the TMEM base address (uint32) at byte 200.
 
-__device__ __noinline__ void list_insert(float s, int32_t id, float* ls, int32_t* li, int k, float* thr) {
+__device__ __noinline__ float list_insert(float s, int32_t id, float* ls, int32_t* li, int k) {
   // ls/li point at this row's column of the [k][128] arrays.  Entries are sorted by (score desc, id asc) and the
   // new id is larger than every id already stored, so it goes behind all entries with score >= s.
+  // Returns the row's new k-th best score (the insertion threshold).
   int j = k - 1;
   while (j > 0 && ls[(j - 1) * kBlockM] < s) {
     ls[j * kBlockM] = ls[(j - 1) * kBlockM];
@@ -87,7 +88,61 @@ __device__ __noinline__ void list_insert(float s, int32_t id, float* ls, int32_t
   }
   ls[j * kBlockM] = s;
   li[j * kBlockM] = id;
-  *thr = ls[(k - 1) * kBlockM];
+  return ls[(k - 1) * kBlockM];
+}
+
+// 16-byte shared-memory load through the shared window (keeps the hot loop on LDS instead of generic LD)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Scores one 32-column chunk held in r[] (raw accumulators in, final scores out) and returns the chunk maximum.
+// Branch-free: the 16 LDS.128 and 96 FP ops of a chunk pipeline freely; the rare insert path is taken per chunk.
+__device__ __forceinline__ float score_chunk(uint32_t (&r)[32], uint32_t meta_addr, float su, float ubias) {
+  float cmax = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float4 m = lds128(meta_addr + j * 8);   // {scale_j, bias_j, scale_j+1, bias_j+1}
+    const float s0 = fmaf(__uint_as_float(r[j]), m.x * su, ubias) + m.y;       // (acc*scales + ub) + ib
+    const float s1 = fmaf(__uint_as_float(r[j + 1]), m.z * su, ubias) + m.w;
+    r[j] = __float_as_uint(s0);
+    r[j + 1] = __float_as_uint(s1);
+    cmax = fmaxf(cmax, fmaxf(s0, s1));
+  }
+  return cmax;
+}
+
+// One 32-column chunk of one user row: final scores, then (top-k mode) the rare inserts, or (dense mode) the store.
+template <bool kDense>
+__device__ __forceinline__ void process_chunk(uint32_t (&r)[32], int c, int t, int32_t id0, uint32_t meta_base,
+                                              float su, float ubias, float& thr, float* ls, int32_t* li,
+                                              const TcParams& p, int64_t u, bool u_ok) {
+  const float cmax = score_chunk(r, meta_base + c * 32 * 8, su, ubias);
+  if constexpr (!kDense) {
+    if (cmax > thr) {   // some column of this chunk enters the row's list (probability ~ 32 k / items seen)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(r[j]);
+        if (s > thr) thr = list_insert(s, id0 + c * 32 + j, ls, li, p.k);
+      }
+    }
+  } else {
+    const int64_t i0 = static_cast<int64_t>(t) * kBlockN + c * 32;
+    if (u_ok) {
+      float* dst = p.dense_out + u * p.dense_stride + i0;
+      if (i0 + 32 <= p.n_items && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (i0 + j < p.n_items) dst[j] = __uint_as_float(r[j]);
+      }
+    }
+  }
 }
 
 template <bool kDense>
@@ -254,64 +309,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * kBlockN;
         const int32_t id0 = p.item_id_offset + t * kBlockN;
+        const uint32_t meta_base = smem_u32(meta_s);
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll 1
         for (int c = 0; c < kBlockN / 32; c += 2) {
           tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rb);   // in flight while chunk c is scored
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 m = meta_s[c * 32 + j];
-            const float s = fmaf(__uint_as_float(ra[j]), m.x * su, ubias) + m.y;
-            if constexpr (kDense) {
-              ra[j] = __float_as_uint(s);
-            } else {
-              if (s > thr) list_insert(s, id0 + c * 32 + j, ls, li, p.k, &thr);
-            }
-          }
-          if constexpr (kDense) {
-            const int64_t i0 = static_cast<int64_t>(t) * kBlockN + c * 32;
-            if (u_ok) {
-              float* dst = p.dense_out + u * p.dense_stride + i0;
-              if (i0 + 32 <= p.n_items && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<uint4*>(dst + j) = make_uint4(ra[j], ra[j + 1], ra[j + 2], ra[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (i0 + j < p.n_items) dst[j] = __uint_as_float(ra[j]);
-              }
-            }
-          }
+          process_chunk<kDense>(ra, c, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
           tmem_ld_wait();
           if (c + 2 < kBlockN / 32) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 m = meta_s[(c + 1) * 32 + j];
-            const float s = fmaf(__uint_as_float(rb[j]), m.x * su, ubias) + m.y;
-            if constexpr (kDense) {
-              rb[j] = __float_as_uint(s);
-            } else {
-              if (s > thr) list_insert(s, id0 + (c + 1) * 32 + j, ls, li, p.k, &thr);
-            }
-          }
-          if constexpr (kDense) {
-            const int64_t i0 = static_cast<int64_t>(t) * kBlockN + (c + 1) * 32;
-            if (u_ok) {
-              float* dst = p.dense_out + u * p.dense_stride + i0;
-              if (i0 + 32 <= p.n_items && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<uint4*>(dst + j) = make_uint4(rb[j], rb[j + 1], rb[j + 2], rb[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (i0 + j < p.n_items) dst[j] = __uint_as_float(rb[j]);
-              }
-            }
-          }
+          process_chunk<kDense>(rb, c + 1, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
           tmem_ld_wait();
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp

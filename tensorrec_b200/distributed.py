@@ -23,8 +23,10 @@ def all_gather_candidates(top_scores, top_items, group=None):
     world = dist.get_world_size(group)
     n_users, k = top_scores.shape
     packed = torch.stack([top_scores.contiguous().view(torch.int32), top_items.contiguous()])      # [2, U, k]
-    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int32, device=packed.device)
+    # output = the ranks' buffers concatenated along dim 0 (the layout both NCCL and gloo accept)
+    gathered = torch.empty((world * 2, n_users, k), dtype=torch.int32, device=packed.device)
     dist.all_gather_into_tensor(gathered, packed.contiguous(), group=group)
+    gathered = gathered.view(world, 2, n_users, k)
     scores = gathered[:, 0].view(torch.float32).permute(1, 0, 2).contiguous()                      # [U, world, k]
     items = gathered[:, 1].permute(1, 0, 2).contiguous()
     return scores, items
