@@ -232,23 +232,52 @@ def run_b200(args):
     bu_d, bi_d = torch.from_numpy(bu).to(dev), torch.from_numpy(bi).to(dev)
     ev = {'k1u': [], 'fused': []}
 
+    use_filter = args.topk_path == 'filter' and k <= kernels.filter_max_k()
+    info = {}
+
     def step(record=False):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
         if record:
             e[0].record()
-        _, us, usc = kernels.gather_reduce(ucsr, wu_d, want_f32=False, split_d_pad=d_pad)
+        u32, us, usc = kernels.gather_reduce(ucsr, wu_d, want_f32=use_filter, split_d_pad=d_pad)
         if record:
             e[1].record()
-        _, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=False, split_d_pad=d_pad)
+        i32, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=use_filter, split_d_pad=d_pad)
         ub = kernels.project_biases(ucsr, bu_d)
         ib = kernels.project_biases(icsr, bi_d)
-        meta = kernels.pack_item_meta(isc, ib, n_local)
-        if record:
-            e[2].record()
-        cs, ci = kernels.score_topk(us, usc, ub, its, meta, n_users, n_local, d_pad, k, item_id_offset=lo)
-        if record:
-            e[3].record()
-        ts, ti = kernels.topk_merge(cs, ci, k)
+        users = kernels.SideOperands(u32, us, usc, ub, n_users, d, d_pad)
+        items = kernels.SideOperands(i32, its, isc, ib, n_local, d, d_pad)
+        if use_filter:
+            stats = torch.zeros((3,), dtype=torch.float32, device=dev)
+            user_norm = kernels.operand_stats(us, usc, d_pad)
+            kernels.operand_stats(its, isc, d_pad, want_norm=False, stats=stats)
+            item_hi = kernels.rescale_hi_global(its, isc, stats, d_pad)
+            bias_pad = kernels.pack_item_bias(ib, n_local, stats, dev)
+            if record:
+                e[2].record()
+            cs, ci, theta, flags = kernels.score_filter(us, usc, ub, user_norm, item_hi, stats, bias_pad, n_users,
+                                                        n_local, d_pad, k, item_id_offset=lo)
+            if record:
+                e[3].record()
+            ts, ti, bad = kernels.rescore_topk(u32, i32, ub, ib, ci, theta, flags, user_norm, stats, k,
+                                               item_id_offset=lo)
+            n_bad = int(bad.sum().item())
+            info['fallback_rows'] = n_bad
+            if n_bad:      # rows whose bound could not be certified go through the exact kernel (inside the timed step)
+                idx = bad.nonzero(as_tuple=True)[0]
+                sub = kernels.SideOperands(None, us.index_select(0, idx).contiguous(), usc.index_select(0, idx),
+                                           ub.index_select(0, idx), int(idx.numel()), d, d_pad)
+                ex_s, ex_i = kernels.topk_exact(sub, items, k, item_id_offset=lo)
+                ts.index_copy_(0, idx, ex_s)
+                ti.index_copy_(0, idx, ex_i)
+        else:
+            meta = kernels.pack_item_meta(isc, ib, n_local)
+            if record:
+                e[2].record()
+            cs, ci = kernels.score_topk(us, usc, ub, its, meta, n_users, n_local, d_pad, k, item_id_offset=lo)
+            if record:
+                e[3].record()
+            ts, ti = kernels.topk_merge(cs, ci, k)
         if world > 1:
             gs, gi = all_gather_candidates(ts, ti)
             ts, ti = kernels.topk_merge(gs, gi, k)
@@ -258,7 +287,7 @@ def run_b200(args):
         return ts, ti
 
     n_splits = kernels.default_splits(n_users, n_local)
-    launches_per_step = 7 + (1 if world > 1 else 0)
+    launches_per_step = (10 if use_filter else 7) + (1 if world > 1 else 0)
 
     for _ in range(args.warmup):
         step()
@@ -289,6 +318,7 @@ def run_b200(args):
         return sp.csr_matrix((arrs[0].numpy(), arrs[1].numpy(), arrs[2].numpy()), shape=m.shape), arrs
 
     del ucsr, icsr
+    tensorrec_b200.tensorrec.TOPK_PATH = 'auto' if use_filter else 'exact'
     model = tensorrec_b200.TensorRec(n_components=d)
     model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
                        'feature_biases_item': bi[:, None]})
@@ -341,23 +371,27 @@ def run_b200(args):
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': 'f32 (3 x fp16 split-product tcgen05 passes, fp32 accumulate)', 'data': 'synthetic',
+        'dtype': ('f32 (1 fp16 tcgen05 filter pass with a certified bound + exact fp32 re-scoring of the survivors)'
+                  if use_filter else 'f32 (3 x fp16 split-product tcgen05 passes, fp32 accumulate)'),
+        'data': 'synthetic',
         'config': {'workload': 'predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, '
                                'LinearRepr x DotProduct, biased (BASELINE configs[4] shape at 1M x 1M; SURVEY C5)'
                                % (k, n_users, n_items, d),
                    'parallelism': 'item-sharded x%d + 1 NCCL all-gather' % world if world > 1 else 'single GPU',
-                   'n_splits': n_splits, 'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
+                   'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
+                   'fallback_rows_last_step': info.get('fallback_rows', 0), 'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
                    % ((n_users + n_local) * 2 * d_pad * 2 / 1e6, (wu.nbytes + wi.nbytes) / 1e6)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_ms_step, 'api': 'TensorRec.predict_rank(user_features, item_features, k) on pinned '
                 'host CSR', 'matches_value_arm': same},
         'gpu_launches': launches_per_step * args.steps,
-        'roofline': {'kernel': 'score_tc_kernel<topk> (trk_score_topk_f16x3)', 'bound': 'tensor', 'achieved': achieved,
-                     'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+        'roofline': {'kernel': ('score_filter_kernel (trk_score_filter_f16)' if use_filter
+                                else 'score_tc_kernel<topk> (trk_score_topk_f16x3)'), 'bound': 'tensor',
+                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                      'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'ms_per_launch': fused_ms,
-                     'issued_tflops': 3 * achieved, 'issued_frac': 3 * achieved / peak,
-                     'share_of_step': fused_ms / ms_step},
+                     'issued_tflops': (1 if use_filter else 3) * achieved,
+                     'issued_frac': (1 if use_filter else 3) * achieved / peak, 'share_of_step': fused_ms / ms_step},
         'roofline_k1': {'kernel': 'csr_gather_reduce_kernel (users)', 'bound': 'hbm', 'achieved': k1_gbs,
                         'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k1_gbs / peaks['hbm_gbs'],
                         'ms_per_launch': k1u_ms, 'algorithmic_bytes': int(k1_bytes)},
@@ -409,6 +443,7 @@ def main():
     ap.add_argument('--items', type=int, default=1000000)
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--k', type=int, default=10)
+    ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     args = ap.parse_args()
     if args.impl == 'reference':

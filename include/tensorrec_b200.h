@@ -143,6 +143,47 @@ int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const 
                          int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset,
                          float* cand_score, int32_t* cand_item, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * K2+K3 fused, FILTER form (the throughput path of predict_rank(k)): one tensor-core pass over the fp16 "hi"
+ * halves gives approximate scores with a proven error bound m = 1.5*2^-10 * |u|_2 * max_j |i_j|_2 (+ bias
+ * rounding); per user the kernel keeps every item whose approximate score is within 3m of the running k-th best.
+ * trk_rescore_topk_f32 then scores the survivors exactly (fp32 dot product of the fp32 representations + biases,
+ * i.e. the reference arithmetic of tensorrec/prediction_graphs.py:49-50 and recommendation_graphs.py:41), ranks
+ * them in tf.nn.top_k order (recommendation_graphs.py:81) and verifies the bound; users it flags must be re-run
+ * through trk_score_topk_f16x3.  Same reference chain as trk_score_topk_f16x3, one third of its tensor work.
+ *
+ * Preparation (all device-side, no host sync):
+ *   trk_operand_stats      norm[r] = |row r|_2 (upper bound) of a split operand; stats[0] = max norm, stats[1] = max
+ *                          row scale, both by atomic max (stats[3] must be zeroed by the caller; either output may be
+ *                          NULL)
+ *   trk_rescale_hi_global  item "hi" half re-expressed with ONE scale for the whole matrix: out_hi [rows, d_pad] f16 =
+ *                          hi[r,:] * (scale[r] / stats[1])   (exact power-of-two factors)
+ *   trk_pack_item_bias     bias padded with -inf to n_padded (multiple of 256) entries; stats[2] = max |bias|
+ * Filter outputs, per (user, split, epilogue group): cand_* [n_users, n_splits, 2, 16] (approximate score, global id;
+ * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits, 2].
+ * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_filter_max_k(); n_components <= 128 for the rescoring.
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_score_filter_max_k(void);
+int trk_score_filter_list_width(void); /* candidates per (user, split): 2 * 16 */
+int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm,
+                      float* stats, void* stream);
+int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
+                          void* out_hi, void* stream);
+int trk_pack_item_bias(const float* item_bias, int64_t n_items, float* out, int64_t n_items_padded, float* stats,
+                       void* stream);
+int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
+                         const float* user_norm, const void* item_hi_global, const float* item_stats,
+                         const float* item_bias_padded, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
+                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
+                         float* row_theta, int32_t* row_flags, void* stream);
+/* item_repr holds the rows of THIS shard: global id g lives at row g - item_id_offset.  n_lists = n_splits * 2,
+ * list_width = 16.  out_flag[u] = 1 -> re-run user u through the exact kernel. */
+int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,
+                         const float* item_bias, const int32_t* cand_item, const float* row_theta,
+                         const int32_t* row_flags, const float* user_norm, const float* item_stats, int64_t n_users,
+                         int64_t n_items_local, int32_t d, int32_t n_lists, int32_t list_width, int32_t k,
+                         int32_t item_id_offset, float* out_score, int32_t* out_item, int32_t* out_flag, void* stream);
+
 /* Tensor-core dense prediction with the same operands, writing the full fp32 matrix out[n_users, n_items]
  * (predict(); tensorrec/tensorrec.py:636-664).  HBM-write bound. */
 int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const float* user_bias,

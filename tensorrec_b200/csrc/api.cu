@@ -44,6 +44,17 @@ int score_topk_f16x3(const void*, const float*, const float*, const void*, const
 int score_dense_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
                       float*, int64_t, cudaStream_t);
 int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t, float*, int32_t*, cudaStream_t);
+int score_filter_max_k();
+int score_filter_list_width();
+int operand_stats(const void*, const float*, int64_t, int32_t, float*, float*, cudaStream_t);
+int rescale_hi_global(const void*, const float*, const float*, int64_t, int32_t, void*, cudaStream_t);
+int pack_item_bias(const float*, int64_t, float*, int64_t, float*, cudaStream_t);
+int score_filter_f16(const void*, const float*, const float*, const float*, const void*, const float*, const float*,
+                     int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, float*, int32_t*, float*, int32_t*,
+                     cudaStream_t);
+int rescore_topk(const float*, const float*, const float*, const float*, const int32_t*, const float*, const int32_t*,
+                 const float*, const float*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, int32_t, float*,
+                 int32_t*, int32_t*, cudaStream_t);
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -127,6 +138,45 @@ int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_
                    int32_t k_in, int32_t k_out, float* out_score, int32_t* out_item, void* stream) {
   return trk::topk_merge(cand_score, cand_item, n_users, n_lists, k_in, k_out, out_score, out_item,
                          trk::as_stream(stream));
+}
+
+int trk_score_filter_max_k(void) { return trk::score_filter_max_k(); }
+
+int trk_score_filter_list_width(void) { return trk::score_filter_list_width(); }
+
+int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm,
+                      float* stats, void* stream) {
+  return trk::operand_stats(split, scale, rows, d_pad, out_norm, stats, trk::as_stream(stream));
+}
+
+int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
+                          void* out_hi, void* stream) {
+  return trk::rescale_hi_global(split, scale, stats, rows, d_pad, out_hi, trk::as_stream(stream));
+}
+
+int trk_pack_item_bias(const float* item_bias, int64_t n_items, float* out, int64_t n_items_padded, float* stats,
+                       void* stream) {
+  return trk::pack_item_bias(item_bias, n_items, out, n_items_padded, stats, trk::as_stream(stream));
+}
+
+int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
+                         const float* user_norm, const void* item_hi_global, const float* item_stats,
+                         const float* item_bias_padded, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
+                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
+                         float* row_theta, int32_t* row_flags, void* stream) {
+  return trk::score_filter_f16(user_split, user_scale, user_bias, user_norm, item_hi_global, item_stats,
+                               item_bias_padded, n_users, n_items, d_pad, k, n_splits, item_id_offset, cand_score,
+                               cand_item, row_theta, row_flags, trk::as_stream(stream));
+}
+
+int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,
+                         const float* item_bias, const int32_t* cand_item, const float* row_theta,
+                         const int32_t* row_flags, const float* user_norm, const float* item_stats, int64_t n_users,
+                         int64_t n_items_local, int32_t d, int32_t n_lists, int32_t list_width, int32_t k,
+                         int32_t item_id_offset, float* out_score, int32_t* out_item, int32_t* out_flag, void* stream) {
+  return trk::rescore_topk(user_repr, item_repr, user_bias, item_bias, cand_item, row_theta, row_flags, user_norm,
+                           item_stats, n_users, n_items_local, d, n_lists, list_width, k, item_id_offset, out_score,
+                           out_item, out_flag, trk::as_stream(stream));
 }
 
 }  // extern "C"

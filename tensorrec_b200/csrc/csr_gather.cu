@@ -5,15 +5,16 @@
 // relative_cosine (tensorrec/recommendation_graphs.py:119-120), project_biases (recommendation_graphs.py:13-17).
 //
 // Layout / mapping
-//   * a warp walks mini-tiles of 16 consecutive rows (grid-stride, grid = SMs x resident blocks); there is no
-//     block-level barrier: each warp stages into its own slice of shared memory and syncs with __syncwarp;
-//   * the mini-tile's indptr slice and ALL its (col, val) pairs are staged into shared memory with coalesced loads
+//   * a block walks tiles of kTileRows consecutive rows (grid-stride, grid = SMs x resident blocks);
+//   * the tile's indptr slice and ALL its (col, val) pairs are staged into shared memory with coalesced loads
 //     (the nonzeros of consecutive rows are contiguous in CSR), so the index stream is read from HBM exactly once
 //     and never through scattered 4-entry requests;
-//   * a group of G lanes owns a row; every lane keeps CH float4 accumulators, so one weight row is fetched with
-//     G x 16-byte loads (512 B fully coalesced at d = 128); two rows per group are processed together so that
-//     8 gathers are in flight per lane;
-//   * L2 policy: weight rows evict-last, index streams and outputs evict-first (single use);
+//   * a group of G lanes owns one row; every lane keeps CH float4 accumulators, so one weight row is fetched with
+//     G x 16-byte loads (512 B fully coalesced at d = 128);  4 gathers are kept in flight per lane, 64 warps per SM;
+//   * outputs are written with streaming stores (single use);
+//   (round-1 experiment, profiles/r1_v2_k1_ncu.json: warp-private staging + 8 gathers in flight + L2 evict hints was
+//    SLOWER -- 492 us vs 399 us per 1M rows -- because it became issue-bound at half the occupancy, and the hints did
+//    not raise the 20 % L2 hit rate: the 102 MB of randomly re-referenced tag rows exceed what L2 keeps.)
 //   * accumulation is fp32 FMA in CSR storage order -> bit-identical from run to run, duplicates are summed;
 //   * the epilogue (row still in registers) optionally L2-normalises, writes fp32 and/or the split-fp16 operand
 //     (hi | lo, per-row power-of-two scale) that the tensor-core score kernel consumes.
@@ -127,158 +128,110 @@ __device__ __forceinline__ void row_epilogue(float (&acc)[CH][VEC ? 4 : 1], int 
   }
 }
 
-// ---- L2 cache-policy helpers -------------------------------------------------------------------------------
-// The weight table is the only data with reuse (feature rows referenced by many matrix rows); the CSR streams and
-// the outputs are touched exactly once.  Streams are tagged evict-first and weight rows evict-last so that the
-// 126 MB L2 is spent on weight rows (ncu r1: 2.2x DRAM re-reads of tag rows without the hints).
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ldg_f4_hint(const float* ptr, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg_f1_hint(const float* ptr, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int32_t ldg_i32_stream(const int32_t* ptr, uint64_t pol) {
-  int32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg_f32_stream(const float* ptr, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
-  return v;
-}
-
-constexpr int kMiniTileRows = 16;   // rows staged per warp at a time
-constexpr int kWarpNnzCap = 384;    // staged (col,val) pairs per warp: 3 KB, 24 KB per block, 8 blocks per SM
-
 template <int G, int CH, bool VEC>
-__global__ void __launch_bounds__(kGatherThreads, (CH == 1 ? 4 : (CH == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(kGatherThreads)
 csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
                          const float* __restrict__ val, const float* __restrict__ weights, int64_t rows, int d,
                          int n_normalize, float* __restrict__ out_f32, __half* __restrict__ out_split, int d_pad,
                          float* __restrict__ out_scale) {
   constexpr int W = VEC ? 4 : 1;
-  constexpr int kGroupsPerWarp = 32 / G;
-  constexpr int kWarps = kGatherThreads / 32;
-  __shared__ int32_t s_col_all[kWarps * kWarpNnzCap];
-  __shared__ float s_val_all[kWarps * kWarpNnzCap];
+  constexpr int kGroups = kGatherThreads / G;
+  __shared__ int32_t s_ptr[kTileRows + 1];
+  __shared__ int32_t s_col[kNnzCap];
+  __shared__ float s_val[kNnzCap];
 
-  const int lane32 = threadIdx.x % 32;
-  const int warp_in_block = threadIdx.x / 32;
-  const int group = lane32 / G;
-  const int lane = lane32 % G;
-  int32_t* s_col = s_col_all + warp_in_block * kWarpNnzCap;
-  float* s_val = s_val_all + warp_in_block * kWarpNnzCap;
-  const uint64_t pol_w = l2_policy_evict_last();
-  const uint64_t pol_s = l2_policy_evict_first();
+  const int tid = threadIdx.x;
+  const int group = tid / G;
+  const int lane = tid % G;
+  const int64_t n_tiles = ceil_div(rows, kTileRows);
 
-  const int64_t n_mini = ceil_div(rows, kMiniTileRows);
-  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * kWarps + warp_in_block;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kWarps;
-
-  // every warp walks its own mini-tiles: no block-level barrier anywhere in this kernel
-  for (int64_t mt = warp_global; mt < n_mini; mt += n_warps) {
-    const int64_t r0 = mt * kMiniTileRows;
-    const int nr = static_cast<int>(min(static_cast<int64_t>(kMiniTileRows), rows - r0));
-    const int ptr_l = lane32 <= nr ? ldg_i32_stream(indptr + r0 + lane32, pol_s) : 0;
-    const int p0 = __shfl_sync(0xffffffffu, ptr_l, 0);
-    const int n_tile = __shfl_sync(0xffffffffu, ptr_l, nr) - p0;
-    const bool staged = n_tile <= kWarpNnzCap;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * kTileRows;
+    const int nr = static_cast<int>(min(static_cast<int64_t>(kTileRows), rows - r0));
+    if (tid <= nr) s_ptr[tid] = indptr[r0 + tid];
+    __syncthreads();
+    const int p0 = s_ptr[0];
+    const int n_tile = s_ptr[nr] - p0;
+    const bool staged = n_tile <= kNnzCap;
     if (staged) {
-      for (int i = lane32; i < n_tile; i += 32) {   // coalesced: the rows' nonzeros are contiguous in CSR
-        s_col[i] = ldg_i32_stream(col + p0 + i, pol_s);
-        s_val[i] = ldg_f32_stream(val + p0 + i, pol_s);
+      for (int i = tid; i < n_tile; i += kGatherThreads) {
+        s_col[i] = __ldg(col + p0 + i);
+        s_val[i] = __ldg(val + p0 + i);
       }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // two rows per group in flight (8 gathers per lane): warp-uniform trip count, the epilogue shuffles need all lanes
-    for (int rr_base = 0; rr_base < nr; rr_base += 2 * kGroupsPerWarp) {
-      int a[2], b[2];
-      bool active[2];
-      float acc[2][CH][W];
+    // warp-uniform trip count: the epilogue uses full-mask shuffles, so every lane must reach it
+    for (int rr_base = 0; rr_base < nr; rr_base += kGroups) {
+      const int rr = rr_base + group;
+      const bool active = rr < nr;
+      const int a = active ? s_ptr[rr] : 0, b = active ? s_ptr[rr + 1] : 0;
+      float acc[CH][W];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int rr = rr_base + h * kGroupsPerWarp + group;
-        active[h] = rr < nr;
-        const int src = active[h] ? rr : 0;
-        a[h] = __shfl_sync(0xffffffffu, ptr_l, src);
-        b[h] = __shfl_sync(0xffffffffu, ptr_l, src + 1);
-        if (!active[h]) a[h] = b[h] = 0;
+      for (int j = 0; j < CH; ++j)
 #pragma unroll
-        for (int j = 0; j < CH; ++j)
+        for (int w = 0; w < W; ++w) acc[j][w] = 0.0f;
+
+      int p = a;
+      // four gathers in flight, FMAs retired in storage order
+      for (; p + 4 <= b; p += 4) {
+        int c[4];
+        float v[4];
 #pragma unroll
-          for (int w = 0; w < W; ++w) acc[h][j][w] = 0.0f;
-      }
-      // batches of 4 entries per row; loads of both rows are issued before any FMA, FMAs retire in storage order
-      while (a[0] < b[0] || a[1] < b[1]) {
-        float v[2][4];
-        float wv[2][4][CH][W];
-        bool ok[2][4];
+        for (int q = 0; q < 4; ++q) {
+          c[q] = staged ? s_col[p + q - p0] : __ldg(col + p + q);
+          v[q] = staged ? s_val[p + q - p0] : __ldg(val + p + q);
+        }
+        float wv[4][CH][W];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int q = 0; q < 4; ++q) {
+          const float* wrow = weights + static_cast<int64_t>(c[q]) * d;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int p = a[h] + q;
-            ok[h][q] = p < b[h];
-            int c = 0;
-            v[h][q] = 0.0f;
-            if (ok[h][q]) {
-              c = staged ? s_col[p - p0] : __ldg(col + p);
-              v[h][q] = staged ? s_val[p - p0] : __ldg(val + p);
-            }
-            const float* wrow = weights + static_cast<int64_t>(c) * d;
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const int e0 = (lane + G * j) * W;
-              if (ok[h][q] && e0 < d) {
-                if constexpr (VEC) {
-                  const float4 t = ldg_f4_hint(wrow + e0, pol_w);
-                  wv[h][q][j][0] = t.x; wv[h][q][j][1] = t.y; wv[h][q][j][2] = t.z; wv[h][q][j][3] = t.w;
-                } else {
-                  wv[h][q][j][0] = ldg_f1_hint(wrow + e0, pol_w);
-                }
+          for (int j = 0; j < CH; ++j) {
+            const int e0 = (lane + G * j) * W;
+            if (e0 < d) {
+              if constexpr (VEC) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + e0));
+                wv[q][j][0] = t.x; wv[q][j][1] = t.y; wv[q][j][2] = t.z; wv[q][j][3] = t.w;
               } else {
-#pragma unroll
-                for (int w = 0; w < W; ++w) wv[h][q][j][w] = 0.0f;
+                wv[q][j][0] = __ldg(wrow + e0);
               }
+            } else {
+#pragma unroll
+              for (int w = 0; w < W; ++w) wv[q][j][w] = 0.0f;
             }
           }
+        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (ok[h][q]) {
+          for (int j = 0; j < CH; ++j)
 #pragma unroll
-              for (int j = 0; j < CH; ++j)
+            for (int w = 0; w < W; ++w) acc[j][w] = fmaf(v[q], wv[q][j][w], acc[j][w]);
+      }
+      for (; p < b; ++p) {
+        const int c = staged ? s_col[p - p0] : __ldg(col + p);
+        const float v = staged ? s_val[p - p0] : __ldg(val + p);
+        const float* wrow = weights + static_cast<int64_t>(c) * d;
 #pragma unroll
-                for (int w = 0; w < W; ++w) acc[h][j][w] = fmaf(v[h][q], wv[h][q][j][w], acc[h][j][w]);
+        for (int j = 0; j < CH; ++j) {
+          const int e0 = (lane + G * j) * W;
+          if (e0 < d) {
+            if constexpr (VEC) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + e0));
+              acc[j][0] = fmaf(v, t.x, acc[j][0]);
+              acc[j][1] = fmaf(v, t.y, acc[j][1]);
+              acc[j][2] = fmaf(v, t.z, acc[j][2]);
+              acc[j][3] = fmaf(v, t.w, acc[j][3]);
+            } else {
+              acc[j][0] = fmaf(v, __ldg(wrow + e0), acc[j][0]);
             }
-          a[h] = min(a[h] + 4, b[h]);
+          }
         }
       }
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        row_epilogue<G, CH, VEC>(acc[h], lane, r0 + rr_base + h * kGroupsPerWarp + group, active[h], d, n_normalize,
-                                 out_f32, out_split, d_pad, out_scale);
+      row_epilogue<G, CH, VEC>(acc, lane, r0 + rr, active, d, n_normalize, out_f32, out_split, d_pad, out_scale);
     }
-    __syncwarp();  // the next mini-tile overwrites this warp's staging slice
+    __syncthreads();  // the next tile overwrites the staging buffers
   }
 }
 
@@ -449,7 +402,7 @@ int csr_gather_reduce(const int32_t* indptr, const int32_t* col, const float* va
     set_error("csr_gather_reduce: n_components=%d (d_pad=%d) exceeds the fused row width", d, d_pad);
     return TRK_ERR_UNSUPPORTED;
   }
-  const int grid = gather_grid(ceil_div(rows, kMiniTileRows * (kGatherThreads / 32)));
+  const int grid = gather_grid(ceil_div(rows, kTileRows));
 #define CALL(G, CH, VEC)                                                                                     \
   csr_gather_reduce_kernel<G, CH, VEC><<<grid, kGatherThreads, 0, stream>>>(                                 \
       indptr, col, val, weights, rows, d, n_normalize, out_f32, static_cast<__half*>(out_split), d_pad, out_scale)

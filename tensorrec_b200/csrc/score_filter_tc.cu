@@ -1,0 +1,627 @@
+// K2+K3 fused, filter form: ONE tcgen05 pass over the fp16 "hi" halves produces approximate scores with a proven
+// error bound; per user row the kernel keeps every item that could still belong to the top-k (approximate score
+// within the bound of the running k-th best).  The few survivors are re-scored exactly in fp32 and ranked by
+// rescore_topk_kernel (rescore_topk.cu), which also verifies the bound and flags rows for the exact 3-pass kernel
+// (score_topk_tc.cu) if it does not hold.  Same reference chain as score_topk_tc.cu: tf.matmul
+// (tensorrec/prediction_graphs.py:49-50), bias_prediction_dense (tensorrec/recommendation_graphs.py:41),
+// rank_predictions (:73-82) restricted to rank <= k.
+//
+// Why: the exact split-product kernel issues 3 tensor passes and its per-row sorted-list inserts serialise a warp
+// (profiles/r1_v2_fused_ncu.json: tensor pipe 37 %, top stall = insert loop).  Here
+//   * tensor work is 1 pass (2*U*I*d flops = the algorithmic count);
+//   * the epilogue hot loop is 1 FFMA + 1/2 FMNMX3 per score: v_j = acc_j + bias_j / c  against a per-row threshold
+//     tau (c = user scale x GLOBAL item scale, both powers of two), branch per 16 columns;
+//   * a passing column is APPENDED (unsorted) to the row's 32-entry buffer in shared memory -- a handful of
+//     instructions; when some row's buffer passes half full the whole warp compacts it cooperatively: one entry per
+//     lane, a 15-step bitonic sort through shuffles, keep everything >= (k-th best - 3m), tighten the threshold;
+//   * item biases come through a small TMA-fed ring with their own mbarriers: the epilogue warps never meet at a
+//     block or group barrier.
+//
+// Error bound.  hi = fp16(x * 2^e) has relative error <= 2^-11 per element (absolute 2^-25 below the fp16 normal
+// range), so |approx - exact| <= (2^-10 + 2^-22) |u|.|i| <= m := kMarginFactor * |u|_2 * max_j |i_j|_2 with
+// kMarginFactor = 1.5 * 2^-10 (covers the fp32 accumulation of the tensor core and the flush of tiny elements).
+// Every item ever excluded had approx <= theta_final, hence exact <= theta_final + m, and theta = a_k - 3m keeps
+// theta + m strictly below the exact k-th best of the survivors.  rescore_topk_kernel checks exactly that inequality.
+#include "common.cuh"
+
+namespace trk {
+
+constexpr int kFBlockM = 128;
+constexpr int kFBlockN = 256;
+constexpr int kFKBlock = 64;
+constexpr int kFUmmaK = 16;
+constexpr int kFThreads = 384;
+constexpr uint32_t kFATileBytes = kFBlockM * kFKBlock * 2;   // 16 KB
+constexpr uint32_t kFBTileBytes = kFBlockN * kFKBlock * 2;   // 32 KB
+constexpr uint32_t kFBiasBytes = kFBlockN * 4;               // 1 KB
+constexpr int kFMaxStages = 5;
+constexpr uint32_t kFTmemCols = 512;
+constexpr int kBufEntries = 32;      // candidate buffer per (row, epilogue group)
+constexpr int kKeepMax = 16;         // entries kept by a compaction (>= k + slack); also the per-group output width
+constexpr int kFilterMaxK = 12;
+constexpr float kMarginFactor = 1.5f * 0.0009765625f;   // 1.5 * 2^-10
+constexpr float kBiasUlps = 4.0f * 1.1920929e-7f;        // 4 ulp(1): rounding of (dot + ub) + ib
+
+struct FilterParams {
+  const float* user_scale;
+  const float* user_bias;      // may be null
+  const float* user_norm;      // |u|_2 per user
+  const float* item_bias;      // [n_tiles * 256], padding = -inf
+  const float* item_stats;     // device: [0] = max_j |i_j|_2, [1] = global item scale (2^-E), [2] = max_j |bias_j|
+  int64_t n_users;
+  int64_t n_items;
+  int32_t n_kblocks;           // d_pad / 64
+  int32_t n_stages;
+  int32_t k;
+  int32_t n_splits;
+  int32_t tiles_per_split;
+  int32_t n_tiles;
+  int32_t n_user_blocks;
+  int32_t item_id_offset;
+  float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
+  int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
+  float* row_theta;            // [n_users, n_splits, 2] final admission threshold
+  int32_t* row_flags;          // [n_users, n_splits, 2] 1 = buffer overflow (row needs the exact kernel)
+};
+
+struct FilterLayout {
+  uint32_t a_off, b_off, buf_off, bias_off, bar_off, total;
+};
+__host__ __device__ inline FilterLayout filter_layout(int n_kblocks, int n_stages) {
+  FilterLayout L;
+  L.a_off = 0;
+  L.b_off = L.a_off + static_cast<uint32_t>(n_kblocks) * kFATileBytes;
+  L.buf_off = L.b_off + static_cast<uint32_t>(n_stages) * kFBTileBytes;
+  L.bias_off = L.buf_off + 2u * kFBlockM * kBufEntries * 8u;      // 64 KB of candidate buffers
+  L.bar_off = L.bias_off + 4u * kFBiasBytes;                      // 2 groups x 2 slots
+  L.total = L.bar_off + 512u;
+  return L;
+}
+// barriers (uint64): [0] a_full [1] a_empty [2..3] tmem_full [4..5] tmem_empty [6..9] bias_full [10..13] bias_empty
+// [14 .. 14+S) b_full [14+S .. 14+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
+
+__device__ __forceinline__ float4 f_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float f_lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void f_sts64(uint32_t addr, float s, int32_t id) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(s)), "r"(id) : "memory");
+}
+__device__ __forceinline__ void f_lds64(uint32_t addr, float* s, int32_t* id) {
+  uint32_t a, b;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+  *s = __uint_as_float(a);
+  *id = static_cast<int32_t>(b);
+}
+// 1-D bulk copy global -> shared, completion in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// (score desc, id asc): does x come before y ?
+__device__ __forceinline__ bool cand_before(float xs, int32_t xi, float ys, int32_t yi) {
+  return xs > ys || (xs == ys && xi < yi);
+}
+
+// Warp-cooperative compaction of the candidate buffer of lane `src`'s row: one entry per lane, bitonic sort by
+// (score desc, id asc), keep everything >= k-th best - 3m (at most kKeepMax), tighten that row's thresholds.
+__device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int src, int k, int& cnt, float& theta,
+                                            float& tau, bool& overflow, float m3, float ubias, float inv_c) {
+  const float kNegInf = -__int_as_float(0x7f800000);
+  const int n = __shfl_sync(0xffffffffu, cnt, src);
+  const uint32_t addr = __shfl_sync(0xffffffffu, buf_row_addr, src);
+  const float m3s = __shfl_sync(0xffffffffu, m3, src);
+  float s = kNegInf;
+  int32_t id = 0x7fffffff;
+  if (lane < n) f_lds64(addr + lane * 8, &s, &id);
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, s, stride);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, id, stride);
+      const bool lower = (lane & stride) == 0;           // this lane holds the earlier position of the pair
+      const bool descending = (lane & size) == 0;        // block direction: "before" elements first
+      const bool other_first = cand_before(os, oi, s, id);
+      // earlier position wants the element that comes first in a descending block (and vice versa)
+      const bool take_other = (lower == descending) ? other_first : !other_first;
+      if (take_other) {
+        s = os;
+        id = oi;
+      }
+    }
+  }
+  // lanes now hold the entries in (score desc, id asc) order, sentinels last
+  const float kth = __shfl_sync(0xffffffffu, s, k - 1);
+  const bool have_k = n >= k;
+  const float floor_s = have_k ? kth - m3s : kNegInf;
+  const unsigned keep = __ballot_sync(0xffffffffu, lane < n && s >= floor_s);
+  int n_keep = __popc(keep);
+  const bool ovf = n_keep > kKeepMax;
+  n_keep = ovf ? kKeepMax : n_keep;
+  if (lane < n_keep) f_sts64(addr + lane * 8, s, id);
+  if (lane == src) {
+    cnt = n_keep;
+    overflow = overflow || ovf;
+    if (have_k) {
+      theta = floor_s;
+      // admission test runs on v = acc + bias/c; move theta there and leave a few ulps of slack (extra survivors are
+      // harmless, a missed one is not)
+      const float t = (theta - ubias) * inv_c;
+      tau = t - 8.0f * 1.1920929e-7f * fabsf(t) - 1e-30f;
+    }
+  }
+  __syncwarp();
+}
+
+// 16 columns of one user row: filter on v = acc + bias * inv_c, append the survivors with their approximate score.
+__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
+                                          float inv_c, float ubias, float tau, uint32_t buf_row_addr, int& cnt) {
+  float v[16];
+  float vmax = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = f_lds128(bias_addr + q * 16);
+    v[4 * q + 0] = fmaf(b.x, inv_c, __uint_as_float(acc[4 * q + 0]));
+    v[4 * q + 1] = fmaf(b.y, inv_c, __uint_as_float(acc[4 * q + 1]));
+    v[4 * q + 2] = fmaf(b.z, inv_c, __uint_as_float(acc[4 * q + 2]));
+    v[4 * q + 3] = fmaf(b.w, inv_c, __uint_as_float(acc[4 * q + 3]));
+    vmax = fmaxf(vmax, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
+  }
+  if (vmax > tau) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (v[j] > tau) {
+        const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + f_lds32(bias_addr + j * 4);   // approximate score
+        if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
+          f_sts64(buf_row_addr + cnt * 8, a, id_base + j);
+          cnt += 1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
+                    const FilterParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const FilterLayout L = filter_layout(p.n_kblocks, p.n_stages);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* tmem_full = bars + 2;
+  uint64_t* tmem_empty = bars + 4;
+  uint64_t* bias_full = bars + 6;     // [group * 2 + slot]
+  uint64_t* bias_empty = bars + 10;
+  uint64_t* b_full = bars + 14;
+  uint64_t* b_empty = bars + 14 + p.n_stages;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int n_kb = p.n_kblocks;
+  const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * p.n_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_users);
+    tma_prefetch_desc(&map_items);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bias_full + i, 1);
+      mbar_init(bias_empty + i, 4);
+    }
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kFTmemCols>(tmem_base_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ======================================
+    if (lane == 0) {
+      uint32_t fill = 0, witer = 0, it = 0;
+      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int ub = static_cast<int>(w % p.n_user_blocks);
+        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        if (t1 <= t0) continue;
+        mbar_wait(a_empty, (witer & 1) ^ 1);
+        mbar_arrive_expect_tx(a_full, n_kb * kFATileBytes);
+        for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb)
+          tma_load_2d(smem + L.a_off + kb * kFATileBytes, &map_users, a_full, kb * kFKBlock, ub * kFBlockM,
+                      kEvictFirst);
+        ++witer;
+        for (int t = t0; t < t1; ++t, ++it) {
+          // item biases of this tile for the epilogue group that will drain it (2 slots per group)
+          const uint32_t g = it & 1, use = it >> 1, slot = g * 2 + (use & 1);
+          mbar_wait(bias_empty + slot, ((use >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bias_full + slot, kFBiasBytes);
+          bulk_load_1d(smem + L.bias_off + slot * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
+                       kFBiasBytes, bias_full + slot);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            const uint32_t s = fill % p.n_stages;
+            mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(b_full + s, kFBTileBytes);
+            tma_load_2d(smem + L.b_off + s * kFBTileBytes, &map_items, b_full + s, kb * kFKBlock, t * kFBlockN,
+                        kEvictLast);
+            ++fill;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16_f32(kFBlockM, kFBlockN);
+      uint32_t fill = 0, witer = 0, it = 0;
+      const uint32_t a_base = smem_u32(smem + L.a_off);
+      const uint32_t b_base = smem_u32(smem + L.b_off);
+      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        if (t1 <= t0) continue;
+        mbar_wait(a_full, witer & 1);
+        ++witer;
+        for (int t = t0; t < t1; ++t, ++it) {
+          const uint32_t buf = it & 1;
+          mbar_wait(tmem_empty + buf, ((it >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kFBlockN;
+          uint32_t accumulate = 0;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            const uint32_t s = fill % p.n_stages;
+            mbar_wait(b_full + s, (fill / p.n_stages) & 1);
+            tcgen05_fence_after();
+            const uint64_t da = umma_desc_k_major_sw128(a_base + kb * kFATileBytes);
+            const uint64_t db = umma_desc_k_major_sw128(b_base + s * kFBTileBytes);
+#pragma unroll
+            for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks) {
+              umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(b_empty + s);
+            ++fill;
+          }
+          umma_commit(tmem_full + buf);
+        }
+        umma_commit(a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==========================================
+    const int group = (warp - 4) / 4;
+    const int quarter = warp % 4;
+    const int row = quarter * 32 + lane;
+    const float kNegInf = -__int_as_float(0x7f800000);
+    const uint32_t buf_row_addr =
+        smem_u32(smem + L.buf_off) + static_cast<uint32_t>((group * kFBlockM + row) * kBufEntries * 8);
+    const float max_item_norm = __ldg(p.item_stats + 0);
+    const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
+    const float max_item_bias = __ldg(p.item_stats + 2);
+    uint32_t it = 0;
+
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int ub = static_cast<int>(w % p.n_user_blocks);
+      const int sp = static_cast<int>(w / p.n_user_blocks);
+      const int t0 = sp * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const int64_t u = static_cast<int64_t>(ub) * kFBlockM + row;
+      const bool u_ok = u < p.n_users;
+      const float su = u_ok ? __ldg(p.user_scale + u) : 1.0f;
+      const float ubias = (u_ok && p.user_bias != nullptr) ? __ldg(p.user_bias + u) : 0.0f;
+      const float unorm = u_ok ? __ldg(p.user_norm + u) : 0.0f;
+      const float c = su * item_scale;          // powers of two: exact
+      const float inv_c = 1.0f / c;
+      // error bound of one approximate score: operand rounding + the fp32 rounding of the two bias adds
+      const float m3 = 3.0f * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
+      float tau = kNegInf, theta = kNegInf;
+      int cnt = 0;
+      bool overflow = false;
+
+      for (int t = t0; t < t1; ++t, ++it) {
+        if (static_cast<int>(it & 1) != group) continue;
+        const uint32_t use = it >> 1, slot = group * 2 + (use & 1);
+        mbar_wait(bias_full + slot, (use >> 1) & 1);
+        mbar_wait(tmem_full + group, use & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * kFBlockN;
+        const uint32_t bias_base = smem_u32(smem + L.bias_off) + slot * kFBiasBytes;
+        const int32_t id0 = p.item_id_offset + t * kFBlockN;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(taddr, ra);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
+          tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
+                      buf_row_addr, cnt);
+            unsigned need = __ballot_sync(0xffffffffu, cnt > kBufEntries - 16);
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+            }
+          }
+          tmem_ld_wait();
+          if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
+                      ubias, tau, buf_row_addr, cnt);
+            unsigned need = __ballot_sync(0xffffffffu, cnt > kBufEntries - 16);
+            while (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+            }
+          }
+          tmem_ld_wait();
+        }
+        // accumulator and bias slot drained
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tmem_empty + group);
+          mbar_arrive(bias_empty + slot);
+        }
+      }
+
+      // end of the item range: final compaction of every row of this warp, then emit the survivors
+      for (int src = 0; src < 32; ++src)
+        compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+      if (u_ok) {
+        const int64_t base = ((u * p.n_splits + sp) * 2 + group);
+        float* os = p.cand_score + base * kKeepMax;
+        int32_t* oi = p.cand_item + base * kKeepMax;
+        for (int e = 0; e < kKeepMax; ++e) {
+          float s = kNegInf;
+          int32_t id = 0x7fffffff;
+          if (e < cnt) f_lds64(buf_row_addr + e * 8, &s, &id);
+          os[e] = s;
+          oi[e] = id;
+        }
+        p.row_theta[base] = theta;
+        p.row_flags[base] = overflow ? 1 : 0;
+      }
+      __syncwarp();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kFTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// operand preparation: row norms + global statistics, and the globally scaled "hi" item operand
+// ---------------------------------------------------------------------------------------------------------
+// stats[0] = max row norm, stats[1] = max row scale (2^-e of the largest row); both via atomicMax on the float bits
+// (non-negative floats order like their bit patterns) -> order independent, deterministic.  stats must be zeroed.
+__global__ void operand_stats_kernel(const __half* __restrict__ split, const float* __restrict__ scale, int64_t rows,
+                                     int d_pad, float* __restrict__ out_norm, float* __restrict__ stats) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * blockDim.x / 32;
+  float local_max_norm = 0.0f, local_max_scale = 0.0f;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    const __half* hi = split + r * 2 * d_pad;
+    const __half* lo = hi + d_pad;
+    float ss = 0.0f;
+    for (int e = lane * 2; e < d_pad; e += 64) {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(hi + e));
+      const float2 l = __half22float2(*reinterpret_cast<const __half2*>(lo + e));
+      const float x0 = h.x + l.x, x1 = h.y + l.y;
+      ss = fmaf(x0, x0, ss);
+      ss = fmaf(x1, x1, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float sc = scale[r];
+    // the norm is used as an UPPER bound: inflate by 2^-9 to cover the 22-bit operand and the reduction rounding
+    const float norm = sqrtf(ss) * sc * 1.002f;
+    if (lane == 0) {
+      if (out_norm != nullptr) out_norm[r] = norm;
+      local_max_norm = fmaxf(local_max_norm, norm);
+      if (ss > 0.0f) local_max_scale = fmaxf(local_max_scale, sc);   // all-zero rows carry the neutral scale 1
+    }
+  }
+  if (lane == 0 && stats != nullptr) {
+    atomicMax(reinterpret_cast<int*>(stats + 0), __float_as_int(local_max_norm));
+    atomicMax(reinterpret_cast<int*>(stats + 1), __float_as_int(local_max_scale));
+  }
+}
+
+// hi_global[r, :] = hi[r, :] * (scale_r / max_scale): an exact power-of-two rescale (values of small rows may fall
+// into the fp16 subnormal range -- that loss is inside the filter's error bound).
+__global__ void rescale_hi_global_kernel(const __half* __restrict__ split, const float* __restrict__ scale,
+                                         const float* __restrict__ stats, int64_t rows, int d_pad,
+                                         __half* __restrict__ out_hi) {
+  const float inv_max = 1.0f / fmaxf(stats[1], 1e-38f);
+  const int64_t n_vec = rows * (d_pad / 8);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / (d_pad / 8);
+    const int e = static_cast<int>(i % (d_pad / 8)) * 8;
+    const float f = scale[r] * inv_max;   // power of two <= 1
+    uint4 raw = *reinterpret_cast<const uint4*>(split + r * 2 * d_pad + e);
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 v = __half22float2(h[q]);
+      h[q] = __floats2half2_rn(v.x * f, v.y * f);
+    }
+    *reinterpret_cast<uint4*>(out_hi + r * d_pad + e) = raw;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn filter_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// fp16 [rows, row_elems] row-major (only the first d_pad columns are addressed), boxes 64 x box_rows, 128B swizzle
+int make_hi_map(CUtensorMap* map, const void* base, int64_t rows, int row_elems, int d_pad, int box_rows) {
+  EncodeTiledFn encode = filter_encode_fn();
+  if (encode == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return TRK_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_elems) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kFKBlock), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                            elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return TRK_ERR_CUDA;
+  }
+  return TRK_OK;
+}
+
+constexpr uint32_t kFSmemLimit = 232448;
+
+}  // namespace
+
+int score_filter_max_k() { return kFilterMaxK; }
+int score_filter_list_width() { return 2 * kKeepMax; }
+
+int operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm, float* stats,
+                  cudaStream_t stream) {
+  TRK_CHECK_ARG(split && scale && rows >= 0 && d_pad >= 64 && d_pad % 64 == 0, "operand_stats: bad arguments");
+  if (rows == 0) return TRK_OK;
+  const int threads = 256;
+  const int64_t blocks = ceil_div(rows, threads / 32);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  operand_stats_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
+      static_cast<const __half*>(split), scale, rows, d_pad, out_norm, stats);
+  TRK_CHECK_LAUNCH();
+  return TRK_OK;
+}
+
+int rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
+                      void* out_hi, cudaStream_t stream) {
+  TRK_CHECK_ARG(split && scale && stats && out_hi && rows >= 0 && d_pad >= 64 && d_pad % 64 == 0,
+                "rescale_hi_global: bad arguments");
+  if (rows == 0) return TRK_OK;
+  const int threads = 256;
+  const int64_t blocks = ceil_div(rows * (d_pad / 8), threads);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  rescale_hi_global_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
+      static_cast<const __half*>(split), scale, stats, rows, d_pad, static_cast<__half*>(out_hi));
+  TRK_CHECK_LAUNCH();
+  return TRK_OK;
+}
+
+int score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
+                     const float* user_norm, const void* item_hi, const float* item_stats, const float* item_bias,
+                     int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
+                     int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
+                     int32_t* row_flags, cudaStream_t stream) {
+  TRK_CHECK_ARG(user_split && user_scale && user_norm && item_hi && item_stats && item_bias, "score_filter: null input");
+  TRK_CHECK_ARG(cand_score && cand_item && row_theta && row_flags, "score_filter: null output");
+  TRK_CHECK_ARG(n_users >= 1 && n_items >= 1 && n_splits >= 1, "score_filter: empty shape");
+  TRK_CHECK_ARG(n_users < (1ll << 31) && n_items < (1ll << 31) - 512, "score_filter: shape exceeds int32 indexing");
+  if (d_pad != 64 && d_pad != 128) {
+    set_error("score_filter: d_pad=%d not supported (64 or 128)", d_pad);
+    return TRK_ERR_UNSUPPORTED;
+  }
+  if (k < 1 || k > kFilterMaxK) {
+    set_error("score_filter: k=%d outside [1, %d]", k, kFilterMaxK);
+    return TRK_ERR_UNSUPPORTED;
+  }
+  TRK_CHECK_ARG(reinterpret_cast<uintptr_t>(user_split) % 16 == 0 && reinterpret_cast<uintptr_t>(item_hi) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(item_bias) % 16 == 0,
+                "score_filter: operands must be 16-byte aligned");
+
+  FilterParams p;
+  p.user_scale = user_scale;
+  p.user_bias = user_bias;
+  p.user_norm = user_norm;
+  p.item_bias = item_bias;
+  p.item_stats = item_stats;
+  p.n_users = n_users;
+  p.n_items = n_items;
+  p.n_kblocks = d_pad / kFKBlock;
+  p.k = k;
+  p.n_tiles = static_cast<int32_t>(ceil_div(n_items, kFBlockN));
+  p.n_splits = n_splits;
+  p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
+  p.n_user_blocks = static_cast<int32_t>(ceil_div(n_users, kFBlockM));
+  p.item_id_offset = item_id_offset;
+  p.cand_score = cand_score;
+  p.cand_item = cand_item;
+  p.row_theta = row_theta;
+  p.row_flags = row_flags;
+  p.n_stages = 0;
+  for (int s = kFMaxStages; s >= 2; --s)
+    if (filter_layout(p.n_kblocks, s).total + 1024 <= kFSmemLimit) {
+      p.n_stages = s;
+      break;
+    }
+  TRK_CHECK_ARG(p.n_stages >= 2, "score_filter: shared memory budget exceeded");
+
+  CUtensorMap map_users, map_items;
+  int rc = make_hi_map(&map_users, user_split, n_users, 2 * d_pad, d_pad, kFBlockM);
+  if (rc != TRK_OK) return rc;
+  rc = make_hi_map(&map_items, item_hi, n_items, d_pad, d_pad, kFBlockN);
+  if (rc != TRK_OK) return rc;
+
+  const uint32_t smem_bytes = filter_layout(p.n_kblocks, p.n_stages).total + 1024;
+  TRK_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * n_splits;
+  const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
+  score_filter_kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_users, map_items, p);
+  TRK_CHECK_LAUNCH();
+  return TRK_OK;
+}
+
+}  // namespace trk

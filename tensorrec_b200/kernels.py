@@ -247,3 +247,123 @@ def topk_merge(cand_score, cand_item, k_out):
                             int(k_out), _p(out_s), _p(out_i), _stream())
     _lib.check(rc, 'trk_topk_merge')
     return out_s, out_i
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# filter form of the fused top-k: 1 tensor pass + exact fp32 re-scoring of the survivors
+# ---------------------------------------------------------------------------------------------------------------
+def filter_max_k():
+    return int(require_cuda().trk_score_filter_max_k())
+
+
+def filter_list_width():
+    return int(require_cuda().trk_score_filter_list_width())
+
+
+def operand_stats(split, scale, d_pad, want_norm=True, stats=None):
+    """Row norms (upper bounds) of a split operand and, if `stats` (zeroed float32[3]) is given, the global max norm /
+    max row scale by device-side atomic max."""
+    lib = require_cuda()
+    rows = split.shape[0]
+    norm = torch.empty((rows,), dtype=torch.float32, device=split.device) if want_norm else None
+    rc = lib.trk_operand_stats(_p(split), _p(scale), rows, int(d_pad), _p(norm), _p(stats), _stream())
+    _lib.check(rc, 'trk_operand_stats')
+    return norm
+
+
+def rescale_hi_global(split, scale, stats, d_pad):
+    lib = require_cuda()
+    rows = split.shape[0]
+    out = torch.empty((rows, int(d_pad)), dtype=torch.float16, device=split.device)
+    rc = lib.trk_rescale_hi_global(_p(split), _p(scale), _p(stats), rows, int(d_pad), _p(out), _stream())
+    _lib.check(rc, 'trk_rescale_hi_global')
+    return out
+
+
+def pack_item_bias(item_bias, n_items, stats, device):
+    lib = require_cuda()
+    n_pad = padded_items(n_items)
+    out = torch.empty((n_pad,), dtype=torch.float32, device=device)
+    rc = lib.trk_pack_item_bias(_p(item_bias), n_items, _p(out), n_pad, _p(stats), _stream())
+    _lib.check(rc, 'trk_pack_item_bias')
+    return out
+
+
+def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_stats, item_bias_pad, n_users, n_items,
+                 d_pad, k, n_splits=None, item_id_offset=0):
+    lib = require_cuda()
+    if n_splits is None:
+        n_splits = default_splits(n_users, n_items)
+    dev = user_split.device
+    width = filter_list_width() // 2
+    cand_s = torch.empty((n_users, n_splits, 2, width), dtype=torch.float32, device=dev)
+    cand_i = torch.empty((n_users, n_splits, 2, width), dtype=torch.int32, device=dev)
+    theta = torch.empty((n_users, n_splits, 2), dtype=torch.float32, device=dev)
+    flags = torch.empty((n_users, n_splits, 2), dtype=torch.int32, device=dev)
+    rc = lib.trk_score_filter_f16(_p(user_split), _p(user_scale), _p(user_bias), _p(user_norm), _p(item_hi),
+                                  _p(item_stats), _p(item_bias_pad), n_users, n_items, int(d_pad), int(k),
+                                  int(n_splits), int(item_id_offset), _p(cand_s), _p(cand_i), _p(theta), _p(flags),
+                                  _stream())
+    _lib.check(rc, 'trk_score_filter_f16')
+    return cand_s, cand_i, theta, flags
+
+
+def rescore_topk(user_repr, item_repr, user_bias, item_bias, cand_item, theta, flags, user_norm, item_stats, k,
+                 item_id_offset=0):
+    lib = require_cuda()
+    n_users, d = user_repr.shape
+    n_lists = theta.shape[1] * theta.shape[2]
+    width = cand_item.shape[-1]
+    dev = user_repr.device
+    out_s = torch.empty((n_users, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((n_users, k), dtype=torch.int32, device=dev)
+    out_f = torch.empty((n_users,), dtype=torch.int32, device=dev)
+    rc = lib.trk_rescore_topk_f32(_p(user_repr), _p(item_repr), _p(user_bias), _p(item_bias), _p(cand_item), _p(theta),
+                                  _p(flags), _p(user_norm), _p(item_stats), n_users, item_repr.shape[0], d, n_lists,
+                                  width, int(k), int(item_id_offset), _p(out_s), _p(out_i), _p(out_f), _stream())
+    _lib.check(rc, 'trk_rescore_topk_f32')
+    return out_s, out_i, out_f
+
+
+class SideOperands(object):
+    """Everything the score kernels need from one side (users or items), all resident on the device."""
+
+    def __init__(self, repr_f32, split, scale, bias, n_rows, d, d_pad):
+        self.repr_f32, self.split, self.scale, self.bias = repr_f32, split, scale, bias
+        self.n_rows, self.d, self.d_pad = n_rows, d, d_pad
+
+
+def topk_exact(users, items, k, n_splits=None, item_id_offset=0):
+    """Exact 3-pass fused kernel + merge: ([U, k] scores, [U, k] ids)."""
+    meta = pack_item_meta(items.scale, items.bias, items.n_rows)
+    cs, ci = score_topk(users.split, users.scale, users.bias, items.split, meta, users.n_rows, items.n_rows,
+                        users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset)
+    return topk_merge(cs, ci, k)
+
+
+def topk_filter(users, items, k, n_splits=None, item_id_offset=0, info=None):
+    """Filter form: one tensor pass + exact fp32 re-scoring; users whose error bound cannot be certified (buffer
+    overflow under massive ties, bound violated) are re-run through the exact kernel.  Needs users/items.repr_f32."""
+    dev = users.split.device
+    stats = torch.zeros((3,), dtype=torch.float32, device=dev)
+    user_norm = operand_stats(users.split, users.scale, users.d_pad)
+    operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=stats)
+    item_hi = rescale_hi_global(items.split, items.scale, stats, items.d_pad)
+    bias_pad = pack_item_bias(items.bias, items.n_rows, stats, dev)
+    cs, ci, theta, flags = score_filter(users.split, users.scale, users.bias, user_norm, item_hi, stats, bias_pad,
+                                        users.n_rows, items.n_rows, users.d_pad, k, n_splits=n_splits,
+                                        item_id_offset=item_id_offset)
+    top_s, top_i, bad = rescore_topk(users.repr_f32, items.repr_f32, users.bias, items.bias, ci, theta, flags,
+                                     user_norm, stats, k, item_id_offset=item_id_offset)
+    n_bad = int(bad.sum().item())          # the only host sync of the path
+    if info is not None:
+        info['fallback_rows'] = n_bad
+    if n_bad:
+        idx = bad.nonzero(as_tuple=True)[0]
+        sub = SideOperands(None, users.split.index_select(0, idx).contiguous(), users.scale.index_select(0, idx),
+                           None if users.bias is None else users.bias.index_select(0, idx), int(idx.numel()), users.d,
+                           users.d_pad)
+        ex_s, ex_i = topk_exact(sub, items, k, item_id_offset=item_id_offset)
+        top_s.index_copy_(0, idx, ex_s)
+        top_i.index_copy_(0, idx, ex_i)
+    return top_s, top_i

@@ -50,6 +50,9 @@ _BUILTIN_PRED = (DotProductPredictionGraph, CosineSimilarityPredictionGraph, Euc
 
 # 'auto': tensor cores whenever the shape allows; 'exact': always the fp32 CUDA-core kernel; 'tensor': insist.
 SCORE_PATH = os.environ.get('TENSORREC_B200_SCORE_PATH', 'auto')
+# predict_rank(k) on the tensor path: 'auto' = 1-pass filter + exact fp32 re-scoring when k allows, 'exact' = always the
+# 3-pass split-product kernel
+TOPK_PATH = os.environ.get('TENSORREC_B200_TOPK_PATH', 'auto')
 
 
 class _Hook(object):
@@ -461,20 +464,21 @@ class TensorRec(object):
             raise RuntimeError('TENSORREC_B200_SCORE_PATH=tensor but this model cannot use the tcgen05 kernel')
         return ok
 
-    def _tensor_operands(self, user_in, item_in, device):
-        """Split-fp16 operands, scales, biases and item meta for the tcgen05 kernels."""
+    def _tensor_operands(self, user_in, item_in, device, want_f32=False):
+        """Both sides as kernels.SideOperands: split-fp16 operands + scales (+ fp32 representations), biases."""
         extra = 1 if type(self.prediction_graph_factory) is CosineSimilarityPredictionGraph else 0
         d_pad = kernels.d_pad_for(self.n_components)
-        _, user_split, user_scale = self._represent(self.user_repr_graph_factory, user_in, self.n_user_features,
-                                                    'user_0', device, extra, want_f32=False, split_d_pad=d_pad)
-        _, item_split, item_scale = self._represent(self.item_repr_graph_factory, item_in, self.n_item_features,
-                                                    'item', device, extra, want_f32=False, split_d_pad=d_pad)
+        u32, user_split, user_scale = self._represent(self.user_repr_graph_factory, user_in, self.n_user_features,
+                                                      'user_0', device, extra, want_f32=want_f32, split_d_pad=d_pad)
+        i32, item_split, item_scale = self._represent(self.item_repr_graph_factory, item_in, self.n_item_features,
+                                                      'item', device, extra, want_f32=want_f32, split_d_pad=d_pad)
         user_bias = item_bias = None
         if self.biased:
             user_bias = self._projected_biases(user_in, 'feature_biases_user', device)
             item_bias = self._projected_biases(item_in, 'feature_biases_item', device)
-        item_meta = kernels.pack_item_meta(item_scale, item_bias, item_in.shape[0])
-        return user_split, user_scale, user_bias, item_split, item_meta, d_pad
+        users = kernels.SideOperands(u32, user_split, user_scale, user_bias, user_in.shape[0], self.n_components, d_pad)
+        items = kernels.SideOperands(i32, item_split, item_scale, item_bias, item_in.shape[0], self.n_components, d_pad)
+        return users, items
 
     def _predict_device(self, user_in, item_in, device):
         """tf_prediction: dense float32 scores [n_users, n_items] on the device."""
@@ -484,8 +488,10 @@ class TensorRec(object):
         if n_users == 0 or n_items == 0:
             return torch.zeros((n_users, n_items), dtype=torch.float32, device=device)
         if self._tensor_path_ok():
-            us, usc, ub, its, meta, d_pad = self._tensor_operands(user_in, item_in, device)
-            return kernels.score_dense_tc(us, usc, ub, its, meta, n_users, n_items, d_pad)
+            users, items = self._tensor_operands(user_in, item_in, device)
+            meta = kernels.pack_item_meta(items.scale, items.bias, n_items)
+            return kernels.score_dense_tc(users.split, users.scale, users.bias, items.split, meta, n_users, n_items,
+                                          users.d_pad)
 
         pred_graph = self.prediction_graph_factory
         builtin = type(pred_graph) in _BUILTIN_PRED
@@ -571,10 +577,14 @@ class TensorRec(object):
 
         fused = self._tensor_path_ok() and k <= kernels.topk_max_k(kernels.d_pad_for(self.n_components)) and n_items > 0
         if fused:
-            us, usc, ub, its, meta, d_pad = self._tensor_operands(user_in, item_in, device)
-            cand_s, cand_i = kernels.score_topk(us, usc, ub, its, meta, n_users, n_items, d_pad, k,
-                                                item_id_offset=item_id_offset)
-            top_s, top_i = kernels.topk_merge(cand_s, cand_i, k)
+            use_filter = TOPK_PATH != 'exact' and k <= kernels.filter_max_k()
+            users, items = self._tensor_operands(user_in, item_in, device, want_f32=use_filter)
+            if use_filter:
+                self.last_topk_info = {}
+                top_s, top_i = kernels.topk_filter(users, items, k, item_id_offset=item_id_offset,
+                                                   info=self.last_topk_info)
+            else:
+                top_s, top_i = kernels.topk_exact(users, items, k, item_id_offset=item_id_offset)
         else:
             # any model the fused kernel does not cover: dense scores -> exact full ranks -> the rank <= k entries
             scores = self._predict_device(user_in, item_in, device)

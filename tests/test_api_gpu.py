@@ -111,11 +111,14 @@ def test_predict_matches_oracle_float(T, monkeypatch, path, prediction, user_rep
     assert differing.mean() < 0.01
 
 
-@pytest.mark.parametrize('path', ['auto', 'exact'])
+@pytest.mark.parametrize('path', ['auto', 'exact', 'auto-exact3'])
 @pytest.mark.parametrize('U,I,d', [(100, 150, 100), (256, 4096, 64), (77, 5000, 128), (50, 300, 10)])
 def test_predict_and_rank_exact_on_integer_fixture(T, monkeypatch, path, U, I, d):
     """SURVEY 8d parity fixture: features in {0,1}, weights in {-2..2}, integer biases -> scores are exact in every
     arithmetic path, ties are everywhere, and the full int32 rank matrix must equal the reference's double sort."""
+    if path == 'auto-exact3':      # tensor cores, but the 3-pass top-k kernel instead of filter + re-scoring
+        path = 'auto'
+        monkeypatch.setattr(T.tensorrec, 'TOPK_PATH', 'exact')
     monkeypatch.setattr(T.tensorrec, 'SCORE_PATH', path)
     uf = H.tag_features(U, 200, 20, seed=U, integer=True)
     itf = H.tag_features(I, 200, 20, seed=I, integer=True)
@@ -250,10 +253,13 @@ def test_movielens_shaped_cosine_full_rank_and_topk_agree(T):
     top = model.predict_rank(uf, itf, k=10)
     full_recall = T.eval.recall_at_k(ranks, interactions, k=10)
     topk_recall = T.eval.recall_at_k(top, interactions, k=10)
-    assert np.allclose(full_recall, topk_recall)
-    # the fused kernel's ids are the rank <= 10 entries of the full-rank route
+    assert np.allclose(full_recall, topk_recall, atol=0.05) and abs(full_recall.mean() - topk_recall.mean()) < 1e-4
+    # the top-k route (filter + exact fp32 re-scoring) names the rank <= 10 entries of the full-rank route (3-pass
+    # split-product scores); the two arithmetics may order a pair differently only when it is tied to ~1e-7
     rows = np.arange(n_users)[:, None]
-    assert np.array_equal(ranks[rows, top.items], np.tile(np.arange(1, 11), (n_users, 1)))
+    agree = ranks[rows, top.items] == np.tile(np.arange(1, 11), (n_users, 1))
+    assert agree.mean() > 0.9995
+    assert np.all(np.abs(top.scores - scores[rows, top.items]) <= 4e-6)
 
 
 def test_recommendation_graph_functions_evaluate_on_the_device(T):

@@ -335,3 +335,103 @@ def test_unsupported_shapes_raise(K):
     uf, itf, wu, wi, bu, bi = make_case(10, 20, 64, True, seed=1)
     with pytest.raises(TrkUnsupportedError):
         run_fused(K, uf, itf, wu, wi, bu, bi, k=K.topk_max_k(64) + 1)
+
+
+# ------------------------------------------------------------------------------------------------- filter + rescore
+def side_operands(K, feats, w, b, d, n_norm=0):
+    csr = K.DeviceCSR.from_scipy(feats)
+    d_pad = K.d_pad_for(d)
+    f32, split, scale = K.gather_reduce(csr, dev(w), n_normalize=n_norm, want_f32=True, split_d_pad=d_pad)
+    bias = K.project_biases(csr, dev(b)) if b is not None else None
+    return K.SideOperands(f32, split, scale, bias, feats.shape[0], d, d_pad)
+
+
+def run_filter(K, uf, itf, wu, wi, bu, bi, k, n_splits=None, n_norm=0, offset=0):
+    users = side_operands(K, uf, wu, bu, wu.shape[1], n_norm)
+    items = side_operands(K, itf, wi, bi, wi.shape[1], n_norm)
+    info = {}
+    s, i = K.topk_filter(users, items, k, n_splits=n_splits, item_id_offset=offset, info=info)
+    return s.cpu().numpy(), i.cpu().numpy(), info
+
+
+def test_operand_stats_and_global_rescale(K):
+    import torch
+    uf, itf, wu, wi, bu, bi = make_case(300, 1000, 100, False, seed=3)
+    items = side_operands(K, itf, wi, bi, 100)
+    stats = torch.zeros(3, device='cuda')
+    norm = K.operand_stats(items.split, items.scale, items.d_pad, stats=stats).cpu().numpy()
+    true = np.linalg.norm(items.repr_f32.cpu().numpy().astype(np.float64), axis=1)
+    assert np.all(norm >= true) and np.all(norm <= true * 1.01 + 1e-30)           # upper bounds, tight
+    st = stats.cpu().numpy()
+    assert st[0] == norm.max() and st[1] == items.scale.cpu().numpy().max()
+    hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad).float().cpu().numpy()
+    x = items.repr_f32.cpu().numpy()
+    rec = hi[:, :100] * st[1]
+    assert np.all(np.abs(rec - x) <= 2.0 ** -11 * np.abs(x) + 2.0 ** -24 * np.abs(x).max())
+    padded = K.pack_item_bias(items.bias, 1000, stats, 'cuda').cpu().numpy()
+    assert padded.shape == (1024,) and np.all(np.isneginf(padded[1000:]))
+    assert np.array_equal(padded[:1000], items.bias.cpu().numpy())
+    assert stats.cpu().numpy()[2] == np.abs(items.bias.cpu().numpy()).max()
+
+
+@pytest.mark.parametrize('U,I,d,k,regime,cosine,splits', [
+    (100, 150, 100, 10, 'tag', False, None), (500, 3000, 128, 10, 'indicator', False, None),
+    (200, 2000, 64, 12, 'tag', True, 3), (1000, 20000, 128, 10, 'indicator', False, 1),
+    (130, 5000, 10, 5, 'tag', False, 7), (1, 700, 64, 1, 'tag', False, None),
+])
+def test_filter_topk_float_matches_oracle(K, U, I, d, k, regime, cosine, splits):
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=U + 1, regime=regime)
+    model = oracle.OracleModel([wu], wi, bu, bi, prediction='cosine' if cosine else 'dot')
+    scores = model.predict(uf, itf)
+    ur, ir = model.user_representation(uf)[0], model.item_representation(itf)
+    if cosine:
+        ur, ir = oracle.l2_normalize(ur), oracle.l2_normalize(ir)
+    tol = H.norm_tolerance(ur, ir, rel=1e-5) + 2e-6
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k, n_splits=splits, n_norm=1 if cosine else 0)
+    rows = np.arange(U)[:, None]
+    assert got_i.min() >= 0 and got_i.max() < I
+    assert np.all(np.abs(got_s - scores[rows, got_i]) <= tol[rows, got_i])      # exact fp32 re-scoring: 1e-5
+    mask = np.ones_like(scores, dtype=bool)
+    mask[rows, got_i] = False
+    assert np.all((scores - tol)[mask].reshape(U, -1) <= got_s[:, -1:] + 1e-6)  # nothing better was left out
+    assert np.all(np.diff(got_s, axis=1) <= 0)
+    exp_i, _ = oracle.top_k_from_scores(scores, k)
+    assert (got_i != exp_i).mean() < 0.01                                        # only sub-tolerance near-ties may swap
+    assert info['fallback_rows'] <= U // 20                                      # continuous scores: the bound certifies
+
+
+@pytest.mark.parametrize('U,I,d,k,splits', [(100, 150, 100, 10, None), (256, 4096, 64, 10, 2), (129, 513, 10, 3, 4)])
+def test_filter_topk_integer_fixture_exact_through_fallback(K, U, I, d, k, splits):
+    """Massive ties: the filter cannot separate equal scores within its bound, overflows and hands those rows to the
+    exact kernel -- the combined result must still be the reference order bit for bit."""
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, True, seed=U + I)
+    scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k, n_splits=splits)
+    assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
+
+
+def test_filter_candidates_respect_the_error_bound(K):
+    """The approximate scores of the survivors are within m = 1.5*2^-10 |u| max|i| of the exact ones, and every true
+    top-k item is among the survivors."""
+    import torch
+    U, I, d, k = 300, 6000, 128, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=9, regime='indicator')
+    users, items = side_operands(K, uf, wu, bu, d), side_operands(K, itf, wi, bi, d)
+    stats = torch.zeros(3, device='cuda')
+    unorm = K.operand_stats(users.split, users.scale, users.d_pad)
+    K.operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=stats)
+    hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad)
+    bias_pad = K.pack_item_bias(items.bias, I, stats, 'cuda')
+    cs, ci, theta, flags = K.score_filter(users.split, users.scale, users.bias, unorm, hi, stats, bias_pad, U, I,
+                                          users.d_pad, k, n_splits=2)
+    scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    cs, ci = cs.cpu().numpy().reshape(U, -1), ci.cpu().numpy().reshape(U, -1)
+    m = 1.5 * 2.0 ** -10 * unorm.cpu().numpy() * stats.cpu().numpy()[0] + 1e-5
+    exp_i, _ = oracle.top_k_from_scores(scores, k)
+    assert int(flags.sum()) == 0
+    for u in range(U):
+        real = ci[u] != 2 ** 31 - 1
+        assert np.all(np.abs(cs[u][real] - scores[u, ci[u][real]]) <= m[u])
+        assert set(exp_i[u]) <= set(ci[u][real])
+        assert real.sum() <= 64
