@@ -433,6 +433,56 @@ def run_reference(args):
     }), flush=True)
 
 
+def run_dense(args):
+    """Secondary measurement (BASELINE configs[1] shape, scaled to fit HBM): predict() = K1 x2 + biases + the tensor-core
+    score kernel writing the dense fp32 matrix.  Bound: HBM write, U*I*4 bytes."""
+    import torch
+    from tensorrec_b200 import kernels
+    kernels.require_cuda()
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    uf, itf, wu, wi, bu, bi = make_problem(args)
+    d_pad = kernels.d_pad_for(args.d)
+    ucsr, icsr = kernels.DeviceCSR.from_scipy(uf, device=dev), kernels.DeviceCSR.from_scipy(itf, device=dev)
+    wu_d, wi_d = torch.from_numpy(wu).to(dev), torch.from_numpy(wi).to(dev)
+    bu_d, bi_d = torch.from_numpy(bu).to(dev), torch.from_numpy(bi).to(dev)
+    out = torch.empty((args.users, args.items), dtype=torch.float32, device=dev)
+    ev = []
+
+    def step():
+        _, us, usc = kernels.gather_reduce(ucsr, wu_d, want_f32=False, split_d_pad=d_pad)
+        _, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=False, split_d_pad=d_pad)
+        ub, ib = kernels.project_biases(ucsr, bu_d), kernels.project_biases(icsr, bi_d)
+        meta = kernels.pack_item_meta(isc, ib, args.items)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        kernels.score_dense_tc(us, usc, ub, its, meta, args.users, args.items, d_pad, out=out)
+        b.record()
+        ev.append((a, b))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    del ev[:]
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        step()
+    s1.record()
+    torch.cuda.synchronize()
+    ms = s0.elapsed_time(s1) / args.steps
+    kms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    peaks = measured_peaks()
+    gbs = args.users * float(args.items) * 4 / (kms * 1e-3) / 1e9
+    print(json.dumps({'metric': 'predict_pairs_per_s', 'value': args.users * float(args.items) / (ms * 1e-3),
+                      'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+                      'config': {'workload': 'predict() dense fp32 scores, %d users x %d items, d=%d (BASELINE configs[1] '
+                                             'shape, user axis cut to fit HBM)' % (args.users, args.items, args.d)},
+                      'roofline': {'kernel': 'score_tc_kernel<dense>', 'bound': 'hbm', 'achieved': gbs,
+                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+                                   'ms_per_launch': kms}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -443,10 +493,13 @@ def main():
     ap.add_argument('--items', type=int, default=1000000)
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--k', type=int, default=10)
+    ap.add_argument('--workload', default='topk', choices=['topk', 'dense'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.workload == 'dense':
+        run_dense(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_b200(args)

@@ -13,34 +13,35 @@
 //     tau (c = user scale x GLOBAL item scale, both powers of two), branch per 16 columns;
 //   * a passing column is APPENDED (unsorted) to the row's 32-entry buffer in shared memory -- a handful of
 //     instructions; when some row's buffer passes half full the whole warp compacts it cooperatively: one entry per
-//     lane, a 15-step bitonic sort through shuffles, keep everything >= (k-th best - 3m), tighten the threshold;
+//     lane, a 15-step bitonic sort through shuffles, keep everything >= (k-th best - 2.25m), tighten the threshold;
 //   * item biases come through a small TMA-fed ring with their own mbarriers: the epilogue warps never meet at a
 //     block or group barrier.
 //
 // Error bound.  hi = fp16(x * 2^e) has relative error <= 2^-11 per element (absolute 2^-25 below the fp16 normal
 // range), so |approx - exact| <= (2^-10 + 2^-22) |u|.|i| <= m := kMarginFactor * |u|_2 * max_j |i_j|_2 with
 // kMarginFactor = 1.5 * 2^-10 (covers the fp32 accumulation of the tensor core and the flush of tiny elements).
-// Every item ever excluded had approx <= theta_final, hence exact <= theta_final + m, and theta = a_k - 3m keeps
-// theta + m strictly below the exact k-th best of the survivors.  rescore_topk_kernel checks exactly that inequality.
+// Every item ever excluded had approx <= theta_final, hence exact <= theta_final + m, and theta = a_k - 2.25m keeps
+// theta + m strictly below the exact k-th best of the survivors (which is >= a_k - m).  rescore_topk_kernel checks exactly that inequality.
 #include "common.cuh"
 
 namespace trk {
 
 constexpr int kFBlockM = 128;
-constexpr int kFBlockN = 256;
+constexpr int kFBlockN = 128;          // item tile: 4 accumulators of 128 columns fill the 512 TMEM columns
 constexpr int kFKBlock = 64;
 constexpr int kFUmmaK = 16;
 constexpr int kFThreads = 384;
 constexpr uint32_t kFATileBytes = kFBlockM * kFKBlock * 2;   // 16 KB
-constexpr uint32_t kFBTileBytes = kFBlockN * kFKBlock * 2;   // 32 KB
-constexpr uint32_t kFBiasBytes = kFBlockN * 4;               // 1 KB
-constexpr int kFMaxStages = 5;
+constexpr uint32_t kFBTileBytes = kFBlockN * kFKBlock * 2;   // 16 KB
+constexpr uint32_t kFBiasBytes = kFBlockN * 4;               // 512 B
+constexpr int kFMaxStages = 8;
 constexpr uint32_t kFTmemCols = 512;
 constexpr int kBufEntries = 32;      // candidate buffer per (row, epilogue group)
 constexpr int kKeepMax = 16;         // entries kept by a compaction (>= k + slack); also the per-group output width
 constexpr int kFilterMaxK = 12;
 constexpr float kMarginFactor = 1.5f * 0.0009765625f;   // 1.5 * 2^-10
 constexpr float kBiasUlps = 4.0f * 1.1920929e-7f;        // 4 ulp(1): rounding of (dot + ub) + ib
+constexpr float kThetaMargins = 2.25f;                   // theta = a_k - 2.25 m  (> 2 m is what the proof needs)
 
 struct FilterParams {
   const float* user_scale;
@@ -61,7 +62,7 @@ struct FilterParams {
   float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
   float* row_theta;            // [n_users, n_splits, 2] final admission threshold
-  int32_t* row_flags;          // [n_users, n_splits, 2] 1 = buffer overflow (row needs the exact kernel)
+  int32_t* row_flags;          // [n_users, n_splits, 2] reserved (0); certification happens in rescore_topk_kernel
 };
 
 struct FilterLayout {
@@ -77,8 +78,11 @@ __host__ __device__ inline FilterLayout filter_layout(int n_kblocks, int n_stage
   L.total = L.bar_off + 512u;
   return L;
 }
-// barriers (uint64): [0] a_full [1] a_empty [2..3] tmem_full [4..5] tmem_empty [6..9] bias_full [10..13] bias_empty
-// [14 .. 14+S) b_full [14+S .. 14+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
+// barriers (uint64): [0] a_full [1] a_empty [2..5] tmem_full [6..9] tmem_empty [10..13] bias_full [14..17] bias_empty
+// [18 .. 18+S) b_full [18+S .. 18+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
+// Accumulator / bias slot of tile `it`: group g = it & 1 drains it, use = it >> 1 counts the group's tiles,
+// slot = g * 2 + (use & 1): every group owns two accumulators, so the MMA warp fills one while the group drains the
+// other (with a single accumulator per group the two phases serialise: profiles/r1_v3_filter_ncu.json).
 
 __device__ __forceinline__ float4 f_lds128(uint32_t addr) {
   float4 v;
@@ -113,9 +117,9 @@ __device__ __forceinline__ bool cand_before(float xs, int32_t xi, float ys, int3
 }
 
 // Warp-cooperative compaction of the candidate buffer of lane `src`'s row: one entry per lane, bitonic sort by
-// (score desc, id asc), keep everything >= k-th best - 3m (at most kKeepMax), tighten that row's thresholds.
+// (score desc, id asc), keep everything >= k-th best - 2.25m (at most kKeepMax), tighten that row's thresholds.
 __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int src, int k, int& cnt, float& theta,
-                                            float& tau, bool& overflow, float m3, float ubias, float inv_c) {
+                                            float& tau, float& drop_max, float m3, float ubias, float inv_c) {
   const float kNegInf = -__int_as_float(0x7f800000);
   const int n = __shfl_sync(0xffffffffu, cnt, src);
   const uint32_t addr = __shfl_sync(0xffffffffu, buf_row_addr, src);
@@ -148,10 +152,14 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   int n_keep = __popc(keep);
   const bool ovf = n_keep > kKeepMax;
   n_keep = ovf ? kKeepMax : n_keep;
+  // more than kKeepMax entries crowd within the bound of the k-th best: the surplus is dropped and the best dropped
+  // score is remembered -- it only matters if it is still close to the k-th best at the END of the sweep (the
+  // verification in rescore_topk_kernel compares max(theta, drop_max) + m with the exact k-th best)
+  const float first_dropped = __shfl_sync(0xffffffffu, s, kKeepMax & 31);
   if (lane < n_keep) f_sts64(addr + lane * 8, s, id);
   if (lane == src) {
     cnt = n_keep;
-    overflow = overflow || ovf;
+    if (ovf) drop_max = fmaxf(drop_max, first_dropped);
     if (have_k) {
       theta = floor_s;
       // admission test runs on v = acc + bias/c; move theta there and leave a few ulps of slack (extra survivors are
@@ -200,12 +208,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* tmem_full = bars + 2;
-  uint64_t* tmem_empty = bars + 4;
-  uint64_t* bias_full = bars + 6;     // [group * 2 + slot]
-  uint64_t* bias_empty = bars + 10;
-  uint64_t* b_full = bars + 14;
-  uint64_t* b_empty = bars + 14 + p.n_stages;
+  uint64_t* tmem_full = bars + 2;     // [group * 2 + (use & 1)]
+  uint64_t* tmem_empty = bars + 6;
+  uint64_t* bias_full = bars + 10;
+  uint64_t* bias_empty = bars + 14;
+  uint64_t* b_full = bars + 18;
+  uint64_t* b_empty = bars + 18 + p.n_stages;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
 
   const int warp = threadIdx.x / 32;
@@ -220,11 +228,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, 4);
-    }
-    for (int i = 0; i < 4; ++i) {
       mbar_init(bias_full + i, 1);
       mbar_init(bias_empty + i, 4);
     }
@@ -289,8 +295,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         mbar_wait(a_full, witer & 1);
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t buf = it & 1;
-          mbar_wait(tmem_empty + buf, ((it >> 1) & 1) ^ 1);
+          const uint32_t use = it >> 1, buf = (it & 1) * 2 + (use & 1);
+          mbar_wait(tmem_empty + buf, ((use >> 1) & 1) ^ 1);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kFBlockN;
           uint32_t accumulate = 0;
@@ -339,18 +345,18 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       const float c = su * item_scale;          // powers of two: exact
       const float inv_c = 1.0f / c;
       // error bound of one approximate score: operand rounding + the fp32 rounding of the two bias adds
-      const float m3 = 3.0f * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
+      const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
       float tau = kNegInf, theta = kNegInf;
       int cnt = 0;
-      bool overflow = false;
+      float drop_max = kNegInf;
 
       for (int t = t0; t < t1; ++t, ++it) {
         if (static_cast<int>(it & 1) != group) continue;
         const uint32_t use = it >> 1, slot = group * 2 + (use & 1);
         mbar_wait(bias_full + slot, (use >> 1) & 1);
-        mbar_wait(tmem_full + group, use & 1);
+        mbar_wait(tmem_full + slot, (use >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * kFBlockN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kFBlockN;
         const uint32_t bias_base = smem_u32(smem + L.bias_off) + slot * kFBiasBytes;
         const int32_t id0 = p.item_id_offset + t * kFBlockN;
         uint32_t ra[32], rb[32];
@@ -367,7 +373,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
             while (need) {
               const int src = __ffs(need) - 1;
               need &= need - 1;
-              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
             }
           }
           tmem_ld_wait();
@@ -380,7 +386,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
             while (need) {
               const int src = __ffs(need) - 1;
               need &= need - 1;
-              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+              compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
             }
           }
           tmem_ld_wait();
@@ -389,14 +395,14 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tmem_empty + group);
+          mbar_arrive(tmem_empty + slot);
           mbar_arrive(bias_empty + slot);
         }
       }
 
       // end of the item range: final compaction of every row of this warp, then emit the survivors
       for (int src = 0; src < 32; ++src)
-        compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, overflow, m3, ubias, inv_c);
+        compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
       if (u_ok) {
         const int64_t base = ((u * p.n_splits + sp) * 2 + group);
         float* os = p.cand_score + base * kKeepMax;
@@ -408,8 +414,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
           os[e] = s;
           oi[e] = id;
         }
-        p.row_theta[base] = theta;
-        p.row_flags[base] = overflow ? 1 : 0;
+        p.row_theta[base] = fmaxf(theta, drop_max);   // every excluded item has an approximate score <= this
+        p.row_flags[base] = 0;
       }
       __syncwarp();
     }
