@@ -22,6 +22,8 @@
 // kMarginFactor = 1.5 * 2^-10 (covers the fp32 accumulation of the tensor core and the flush of tiny elements).
 // Every item ever excluded had approx <= theta_final, hence exact <= theta_final + m, and theta = a_k - 2.25m keeps
 // theta + m strictly below the exact k-th best of the survivors (which is >= a_k - m).  rescore_topk_kernel checks exactly that inequality.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace trk {
@@ -59,6 +61,7 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_blocks;
   int32_t item_id_offset;
+  int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain
   float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
   float* row_theta;            // [n_users, n_splits, 2] final admission threshold
@@ -103,14 +106,6 @@ __device__ __forceinline__ void f_lds64(uint32_t addr, float* s, int32_t* id) {
   *s = __uint_as_float(a);
   *id = static_cast<int32_t>(b);
 }
-// 1-D bulk copy global -> shared, completion in bytes on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // (score desc, id asc): does x come before y ?
 __device__ __forceinline__ bool cand_before(float xs, int32_t xi, float ys, int32_t yi) {
   return xs > ys || (xs == ys && xi < yi);
@@ -360,6 +355,18 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         const uint32_t bias_base = smem_u32(smem + L.bias_off) + slot * kFBiasBytes;
         const int32_t id0 = p.item_id_offset + t * kFBlockN;
         uint32_t ra[32], rb[32];
+        if (p.debug_mode == 2) goto drained;
+        if (p.debug_mode == 1) {
+          float acc_dbg = 0.0f;
+          for (int ch = 0; ch < kFBlockN / 32; ++ch) {
+            tmem_ld_32x32b_x32(taddr + ch * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_dbg = fmaxf(acc_dbg, __uint_as_float(ra[j]));
+          }
+          if (acc_dbg == 1.2345e30f) cnt = 1;
+          goto drained;
+        }
         tmem_ld_32x32b_x32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll 1
@@ -391,6 +398,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
           }
           tmem_ld_wait();
         }
+      drained:
         // accumulator and bias slot drained
         tcgen05_fence_before();
         __syncwarp();
@@ -607,6 +615,10 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.cand_item = cand_item;
   p.row_theta = row_theta;
   p.row_flags = row_flags;
+  {
+    const char* dbg = getenv("TRK_FILTER_DEBUG");
+    p.debug_mode = dbg != nullptr ? atoi(dbg) : 0;
+  }
   p.n_stages = 0;
   for (int s = kFMaxStages; s >= 2; --s)
     if (filter_layout(p.n_kblocks, s).total + 1024 <= kFSmemLimit) {

@@ -12,12 +12,12 @@
 //
 // CTA = 384 threads, one CTA per SM, persistent over work items (user block of 128 rows, item split):
 //   warp 0      TMA producer: the A block (all k-blocks, resident for the whole sweep) then a ring of B k-block
-//               tiles [256 items x 64 fp16, 128B-swizzled] over the item range;
-//   warp 1      MMA issuer (one elected thread): M=128, N=256, K=16 instructions, accumulators double-buffered in
-//               TMEM (2 x 256 columns); tcgen05.commit releases smem stages and publishes finished accumulators;
+//               tiles [128 items x 64 fp16, 128B-swizzled] over the item range;
+//   warp 1      MMA issuer (one elected thread): M=128, N=128, K=16 instructions, four 128-column accumulators in
+//               TMEM; tcgen05.commit releases smem stages and publishes finished accumulators;
 //   warp 2      TMEM allocator;
-//   warps 4-7   epilogue group 0, warps 8-11 epilogue group 1: group g drains accumulator buffer g (tiles
-//               alternate), one thread per user row: tcgen05.ld 32 columns at a time, score = acc * scale_u *
+//   warps 4-7   epilogue group 0, warps 8-11 epilogue group 1: tiles alternate between the groups, each group owns two
+//               accumulators and two {scale, bias} slots fed by TMA; one thread per user row: tcgen05.ld 32 columns at a time, score = acc * scale_u *
 //               scale_i + bias_u + bias_i, compare against the row's current k-th best, rare insert into the row's
 //               sorted list in shared memory.  Items are visited in ascending id order and the compare is strict,
 //               so equal scores keep the lower item id first -- tf.nn.top_k's order.
@@ -26,14 +26,15 @@
 namespace trk {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockN = 256;
+constexpr int kBlockN = 128;          // item tile; 4 accumulators of 128 columns fill the 512 TMEM columns
 constexpr int kKBlock = 64;           // fp16 per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kTcThreads = 384;
 constexpr int kEpiThreads = 128;      // per epilogue group
 constexpr uint32_t kATileBytes = kBlockM * kKBlock * 2;   // 16 KB
-constexpr uint32_t kBTileBytes = kBlockN * kKBlock * 2;   // 32 KB
-constexpr int kMaxStages = 6;
+constexpr uint32_t kBTileBytes = kBlockN * kKBlock * 2;   // 16 KB
+constexpr uint32_t kMetaBytes = kBlockN * 8;              // {item scale, item bias} per column: 1 KB per tile
+constexpr int kMaxStages = 10;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxK = 32;
 
@@ -68,13 +69,16 @@ __host__ __device__ inline SmemLayout make_layout(int n_kblocks, int n_stages, i
   L.list_score_off = L.b_off + static_cast<uint32_t>(n_stages) * kBTileBytes;
   L.list_item_off = L.list_score_off + 2u * k * kBlockM * 4u;
   L.meta_off = L.list_item_off + 2u * k * kBlockM * 4u;
-  L.bar_off = L.meta_off + 2u * kBlockN * 8u;
-  L.total = L.bar_off + 256u;
+  L.bar_off = L.meta_off + 4u * kMetaBytes;      // 2 groups x 2 slots, filled by the TMA warp
+  L.total = L.bar_off + 512u;
   return L;
 }
 
-// barrier block (uint64 each): [0] a_full, [1] a_empty, [2..3] tmem_full, [4..5] tmem_empty,
-// [6 .. 6+S) b_full, [6+S .. 6+2S) b_empty; then the TMEM base address (uint32) at byte 200.
+// barrier block (uint64 each): [0] a_full, [1] a_empty, [2..5] tmem_full, [6..9] tmem_empty, [10..13] meta_full,
+// [14..17] meta_empty, [18 .. 18+S) b_full, [18+S .. 18+2S) b_empty; then the TMEM base address (uint32) at byte 400.
+// Tile `it` is drained by epilogue group g = it & 1; use = it >> 1 counts that group's tiles and
+// slot = g * 2 + (use & 1) names its accumulator and meta slot: two accumulators per group, so the MMA warp fills
+// one while the group drains the other.
 
 __device__ __noinline__ float list_insert(float s, int32_t id, float* ls, int32_t* li, int k) {
   // ls/li point at this row's column of the [k][128] arrays.  Entries are sorted by (score desc, id asc) and the
@@ -157,10 +161,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* tmem_full = bars + 2;
-  uint64_t* tmem_empty = bars + 4;
-  uint64_t* b_full = bars + 6;
-  uint64_t* b_empty = bars + 6 + p.n_stages;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 200);
+  uint64_t* tmem_empty = bars + 6;
+  uint64_t* meta_full = bars + 10;
+  uint64_t* meta_empty = bars + 14;
+  uint64_t* b_full = bars + 18;
+  uint64_t* b_empty = bars + 18 + p.n_stages;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -174,9 +180,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, kEpiThreads / 32);
+      mbar_init(meta_full + i, 1);
+      mbar_init(meta_empty + i, kEpiThreads / 32);
     }
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(b_full + i, 1);
@@ -195,6 +203,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     if (lane == 0) {
       uint32_t fill = 0;   // B stages filled so far
       uint32_t witer = 0;  // non-empty work items so far
+      uint32_t it = 0;     // tiles issued so far
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int ub = static_cast<int>(w % p.n_user_blocks);
         const int sp = static_cast<int>(w / p.n_user_blocks);
@@ -207,7 +216,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
           tma_load_2d(smem + L.a_off + kb * kATileBytes, &map_users, a_full, kb * kKBlock, ub * kBlockM,
                       kEvictFirst);
         ++witer;
-        for (int t = t0; t < t1; ++t) {
+        for (int t = t0; t < t1; ++t, ++it) {
+          // {item scale, item bias} of this tile for the epilogue group that will drain it
+          const uint32_t use = it >> 1, slot = (it & 1) * 2 + (use & 1);
+          mbar_wait(meta_empty + slot, ((use >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(meta_full + slot, kMetaBytes);
+          bulk_load_1d(smem + L.meta_off + slot * kMetaBytes, p.item_meta + static_cast<int64_t>(t) * kBlockN,
+                       kMetaBytes, meta_full + slot);
           for (int kb = 0; kb < n_kb2; ++kb) {
             const uint32_t s = fill % p.n_stages;
             mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
@@ -234,8 +249,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         mbar_wait(a_full, witer & 1);
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t buf = it & 1;
-          mbar_wait(tmem_empty + buf, ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+          const uint32_t use = it >> 1, buf = (it & 1) * 2 + (use & 1);
+          mbar_wait(tmem_empty + buf, ((use >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kBlockN;
           uint32_t accumulate = 0;
@@ -272,12 +287,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     const int group = (warp - 4) / 4;               // 0 or 1
     const int quarter = warp % 4;                   // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;            // row inside the user block == TMEM lane
-    const int tig = (warp - 4) % 4 * 32 + lane;     // thread index inside the group
-    float2* meta_s = reinterpret_cast<float2*>(smem + L.meta_off) + group * kBlockN;
     float* ls = reinterpret_cast<float*>(smem + L.list_score_off) + group * (kDense ? 0 : p.k) * kBlockM + row;
     int32_t* li = reinterpret_cast<int32_t*>(smem + L.list_item_off) + group * (kDense ? 0 : p.k) * kBlockM + row;
     const float kNegInf = -__int_as_float(0x7f800000);
-    const uint32_t bar_id = 2 + group;
     uint32_t it = 0;
 
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -299,17 +311,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
 
       for (int t = t0; t < t1; ++t, ++it) {
         if (static_cast<int>(it & 1) != group) continue;
-        // stage this tile's {item scale, item bias}: 256 x float2, two columns per thread
-        const float4 m2 = __ldg(reinterpret_cast<const float4*>(p.item_meta + static_cast<int64_t>(t) * kBlockN) + tig);
-        named_barrier_sync(bar_id, kEpiThreads);   // previous tile's readers are done
-        reinterpret_cast<float4*>(meta_s)[tig] = m2;
-        named_barrier_sync(bar_id, kEpiThreads);
-
-        mbar_wait(tmem_full + group, (it >> 1) & 1);
+        const uint32_t use = it >> 1, slot = group * 2 + (use & 1);
+        mbar_wait(meta_full + slot, (use >> 1) & 1);     // this tile's {item scale, item bias}, put there by TMA
+        mbar_wait(tmem_full + slot, (use >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * kBlockN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kBlockN;
         const int32_t id0 = p.item_id_offset + t * kBlockN;
-        const uint32_t meta_base = smem_u32(meta_s);
+        const uint32_t meta_base = smem_u32(smem + L.meta_off) + slot * kMetaBytes;
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32(taddr, ra);
         tmem_ld_wait();
@@ -325,7 +333,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + group);
+        if (lane == 0) {
+          mbar_arrive(tmem_empty + slot);
+          mbar_arrive(meta_empty + slot);
+        }
       }
 
       if constexpr (!kDense) {
