@@ -6,6 +6,12 @@
 // (tensorrec/prediction_graphs.py:49-50), bias_prediction_dense (tensorrec/recommendation_graphs.py:41),
 // rank_predictions (:73-82) restricted to rank <= k.
 //
+// CTA = 256 user rows (two 128-row blocks A0, A1 resident in shared memory) x a sweep over 128-item tiles: every B tile
+// fetched from L2 feeds two MMAs.  (Measured, scripts/filter_probe.py: with one user block per CTA the kernel is bound
+// by the L2->SM stream of the item operand, 5.7 TB/s, not by the tensor pipe.)  Epilogue group g = warps 4+4g..7+4g
+// drains user block g: one thread per user row, two 128-column accumulators per block (4 x 128 = all 512 TMEM
+// columns) so the MMA warp fills one while the group drains the other.
+//
 // Why: the exact split-product kernel issues 3 tensor passes and its per-row sorted-list inserts serialise a warp
 // (profiles/r1_v2_fused_ncu.json: tensor pipe 37 %, top stall = insert loop).  Here
 //   * tensor work is 1 pass (2*U*I*d flops = the algorithmic count);
@@ -59,13 +65,13 @@ struct FilterParams {
   int32_t n_splits;
   int32_t tiles_per_split;
   int32_t n_tiles;
-  int32_t n_user_blocks;
+  int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain
-  float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
-  int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
-  float* row_theta;            // [n_users, n_splits, 2] final admission threshold
-  int32_t* row_flags;          // [n_users, n_splits, 2] reserved (0); certification happens in rescore_topk_kernel
+  float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
+  int32_t* cand_item;          // [n_users, n_splits, kKeepMax] global ids (sentinel INT32_MAX)
+  float* row_theta;            // [n_users, n_splits] final admission threshold
+  int32_t* row_flags;          // [n_users, n_splits] reserved (0); certification happens in rescore_topk_kernel
 };
 
 struct FilterLayout {
@@ -74,18 +80,19 @@ struct FilterLayout {
 __host__ __device__ inline FilterLayout filter_layout(int n_kblocks, int n_stages) {
   FilterLayout L;
   L.a_off = 0;
-  L.b_off = L.a_off + static_cast<uint32_t>(n_kblocks) * kFATileBytes;
+  L.b_off = L.a_off + 2u * static_cast<uint32_t>(n_kblocks) * kFATileBytes;   // two user blocks
   L.buf_off = L.b_off + static_cast<uint32_t>(n_stages) * kFBTileBytes;
   L.bias_off = L.buf_off + 2u * kFBlockM * kBufEntries * 8u;      // 64 KB of candidate buffers
-  L.bar_off = L.bias_off + 4u * kFBiasBytes;                      // 2 groups x 2 slots
+  L.bar_off = L.bias_off + 2u * kFBiasBytes;                      // one slot per tile parity
   L.total = L.bar_off + 512u;
   return L;
 }
-// barriers (uint64): [0] a_full [1] a_empty [2..5] tmem_full [6..9] tmem_empty [10..13] bias_full [14..17] bias_empty
-// [18 .. 18+S) b_full [18+S .. 18+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
-// Accumulator / bias slot of tile `it`: group g = it & 1 drains it, use = it >> 1 counts the group's tiles,
-// slot = g * 2 + (use & 1): every group owns two accumulators, so the MMA warp fills one while the group drains the
-// other (with a single accumulator per group the two phases serialise: profiles/r1_v3_filter_ncu.json).
+// barriers (uint64): [0] a_full [1] a_empty [2..3] tmem_full [4..5] tmem_empty [6..7] bias_full [8..9] bias_empty
+// [10 .. 10+S) b_full [10+S .. 10+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
+// Tile `it` has parity par = it & 1: its two accumulators (user block 0 / 1) are TMEM slots par*2 + {0,1}, its biases
+// sit in bias slot par; both epilogue groups wait on tmem_full[par] / bias_full[par] and release tmem_empty[par] /
+// bias_empty[par] (8 warp arrivals).  Parity double-buffers the accumulators: the MMA warp fills one pair while the
+// groups drain the other (with a single accumulator per group the two phases serialise: profiles/r1_v3_filter_ncu.json).
 
 __device__ __forceinline__ float4 f_lds128(uint32_t addr) {
   float4 v;
@@ -203,18 +210,18 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* tmem_full = bars + 2;     // [group * 2 + (use & 1)]
-  uint64_t* tmem_empty = bars + 6;
-  uint64_t* bias_full = bars + 10;
-  uint64_t* bias_empty = bars + 14;
-  uint64_t* b_full = bars + 18;
-  uint64_t* b_empty = bars + 18 + p.n_stages;
+  uint64_t* tmem_full = bars + 2;     // [tile parity]
+  uint64_t* tmem_empty = bars + 4;
+  uint64_t* bias_full = bars + 6;
+  uint64_t* bias_empty = bars + 8;
+  uint64_t* b_full = bars + 10;
+  uint64_t* b_empty = bars + 10 + p.n_stages;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int n_kb = p.n_kblocks;
-  const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * p.n_splits;
+  const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * p.n_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_users);
@@ -223,11 +230,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 4);
+      mbar_init(tmem_empty + i, 8);
       mbar_init(bias_full + i, 1);
-      mbar_init(bias_empty + i, 4);
+      mbar_init(bias_empty + i, 8);
     }
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(b_full + i, 1);
@@ -246,24 +253,24 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     if (lane == 0) {
       uint32_t fill = 0, witer = 0, it = 0;
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int ub = static_cast<int>(w % p.n_user_blocks);
-        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int up = static_cast<int>(w % p.n_user_pairs);
+        const int sp = static_cast<int>(w / p.n_user_pairs);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
         mbar_wait(a_empty, (witer & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full, n_kb * kFATileBytes);
-        for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb)
-          tma_load_2d(smem + L.a_off + kb * kFATileBytes, &map_users, a_full, kb * kFKBlock, ub * kFBlockM,
-                      kEvictFirst);
+        mbar_arrive_expect_tx(a_full, 2 * n_kb * kFATileBytes);
+        for (int b = 0; b < 2; ++b)
+          for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb); rows past n_users
+            tma_load_2d(smem + L.a_off + (b * n_kb + kb) * kFATileBytes, &map_users, a_full, kb * kFKBlock,
+                        (up * 2 + b) * kFBlockM, kEvictFirst);   // are zero-filled by TMA
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
-          // item biases of this tile for the epilogue group that will drain it (2 slots per group)
-          const uint32_t g = it & 1, use = it >> 1, slot = g * 2 + (use & 1);
-          mbar_wait(bias_empty + slot, ((use >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(bias_full + slot, kFBiasBytes);
-          bulk_load_1d(smem + L.bias_off + slot * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
-                       kFBiasBytes, bias_full + slot);
+          const uint32_t par = it & 1, use = it >> 1;
+          mbar_wait(bias_empty + par, (use & 1) ^ 1);
+          mbar_arrive_expect_tx(bias_full + par, kFBiasBytes);
+          bulk_load_1d(smem + L.bias_off + par * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
+                       kFBiasBytes, bias_full + par);
           for (int kb = 0; kb < n_kb; ++kb) {
             const uint32_t s = fill % p.n_stages;
             mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
@@ -283,33 +290,35 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       const uint32_t a_base = smem_u32(smem + L.a_off);
       const uint32_t b_base = smem_u32(smem + L.b_off);
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int sp = static_cast<int>(w / p.n_user_pairs);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
         mbar_wait(a_full, witer & 1);
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t use = it >> 1, buf = (it & 1) * 2 + (use & 1);
-          mbar_wait(tmem_empty + buf, ((use >> 1) & 1) ^ 1);
+          const uint32_t par = it & 1, use = it >> 1;
+          mbar_wait(tmem_empty + par, (use & 1) ^ 1);   // both groups have drained this accumulator pair
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * kFBlockN;
           uint32_t accumulate = 0;
           for (int kb = 0; kb < n_kb; ++kb) {
             const uint32_t s = fill % p.n_stages;
             mbar_wait(b_full + s, (fill / p.n_stages) & 1);
             tcgen05_fence_after();
-            const uint64_t da = umma_desc_k_major_sw128(a_base + kb * kFATileBytes);
             const uint64_t db = umma_desc_k_major_sw128(b_base + s * kFBTileBytes);
 #pragma unroll
-            for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks) {
-              umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate);
-              accumulate = 1;
+            for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
+              const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
+              const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
+#pragma unroll
+              for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
+                umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
             }
+            accumulate = 1;
             umma_commit(b_empty + s);
             ++fill;
           }
-          umma_commit(tmem_full + buf);
+          umma_commit(tmem_full + par);
         }
         umma_commit(a_empty);
       }
@@ -320,7 +329,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     const int quarter = warp % 4;
     const int row = quarter * 32 + lane;
     const float kNegInf = -__int_as_float(0x7f800000);
-    const uint32_t buf_row_addr =
+    const uint32_t buf_row_addr =   // group g owns user block g of the pair
         smem_u32(smem + L.buf_off) + static_cast<uint32_t>((group * kFBlockM + row) * kBufEntries * 8);
     const float max_item_norm = __ldg(p.item_stats + 0);
     const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
@@ -328,11 +337,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     uint32_t it = 0;
 
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int ub = static_cast<int>(w % p.n_user_blocks);
-      const int sp = static_cast<int>(w / p.n_user_blocks);
+      const int up = static_cast<int>(w % p.n_user_pairs);
+      const int sp = static_cast<int>(w / p.n_user_pairs);
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-      const int64_t u = static_cast<int64_t>(ub) * kFBlockM + row;
+      const int64_t u = (static_cast<int64_t>(up) * 2 + group) * kFBlockM + row;
       const bool u_ok = u < p.n_users;
       const float su = u_ok ? __ldg(p.user_scale + u) : 1.0f;
       const float ubias = (u_ok && p.user_bias != nullptr) ? __ldg(p.user_bias + u) : 0.0f;
@@ -346,13 +355,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       float drop_max = kNegInf;
 
       for (int t = t0; t < t1; ++t, ++it) {
-        if (static_cast<int>(it & 1) != group) continue;
-        const uint32_t use = it >> 1, slot = group * 2 + (use & 1);
-        mbar_wait(bias_full + slot, (use >> 1) & 1);
-        mbar_wait(tmem_full + slot, (use >> 1) & 1);
+        const uint32_t par = it & 1, use = it >> 1;
+        mbar_wait(bias_full + par, use & 1);
+        mbar_wait(tmem_full + par, use & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kFBlockN;
-        const uint32_t bias_base = smem_u32(smem + L.bias_off) + slot * kFBiasBytes;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (par * 2 + group) * kFBlockN;
+        const uint32_t bias_base = smem_u32(smem + L.bias_off) + par * kFBiasBytes;
         const int32_t id0 = p.item_id_offset + t * kFBlockN;
         uint32_t ra[32], rb[32];
         if (p.debug_mode == 2) goto drained;
@@ -403,8 +411,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tmem_empty + slot);
-          mbar_arrive(bias_empty + slot);
+          mbar_arrive(tmem_empty + par);
+          mbar_arrive(bias_empty + par);
         }
       }
 
@@ -412,7 +420,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       for (int src = 0; src < 32; ++src)
         compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
       if (u_ok) {
-        const int64_t base = ((u * p.n_splits + sp) * 2 + group);
+        const int64_t base = u * p.n_splits + sp;
         float* os = p.cand_score + base * kKeepMax;
         int32_t* oi = p.cand_item + base * kKeepMax;
         for (int e = 0; e < kKeepMax; ++e) {
@@ -546,7 +554,7 @@ constexpr uint32_t kFSmemLimit = 232448;
 }  // namespace
 
 int score_filter_max_k() { return kFilterMaxK; }
-int score_filter_list_width() { return 2 * kKeepMax; }
+int score_filter_list_width() { return kKeepMax; }
 
 int operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm, float* stats,
                   cudaStream_t stream) {
@@ -609,7 +617,7 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.n_tiles = static_cast<int32_t>(ceil_div(n_items, kFBlockN));
   p.n_splits = n_splits;
   p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
-  p.n_user_blocks = static_cast<int32_t>(ceil_div(n_users, kFBlockM));
+  p.n_user_pairs = static_cast<int32_t>(ceil_div(n_users, 2 * kFBlockM));
   p.item_id_offset = item_id_offset;
   p.cand_score = cand_score;
   p.cand_item = cand_item;
@@ -635,7 +643,7 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
 
   const uint32_t smem_bytes = filter_layout(p.n_kblocks, p.n_stages).total + 1024;
   TRK_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * n_splits;
+  const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
   const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
   score_filter_kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_users, map_items, p);
   TRK_CHECK_LAUNCH();
