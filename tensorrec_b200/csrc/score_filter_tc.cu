@@ -250,7 +250,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    {   // warp-uniform control flow, one elected lane issues (see the MMA warp)
       uint32_t fill = 0, witer = 0, it = 0;
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int up = static_cast<int>(w % p.n_user_pairs);
@@ -259,24 +259,33 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
         mbar_wait(a_empty, (witer & 1) ^ 1);
-        mbar_arrive_expect_tx(a_full, 2 * n_kb * kFATileBytes);
-        for (int b = 0; b < 2; ++b)
-          for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb); rows past n_users
-            tma_load_2d(smem + L.a_off + (b * n_kb + kb) * kFATileBytes, &map_users, a_full, kb * kFKBlock,
-                        (up * 2 + b) * kFBlockM, kEvictFirst);   // are zero-filled by TMA
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full, 2 * n_kb * kFATileBytes);
+          for (int b = 0; b < 2; ++b)
+            for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb); rows past
+              tma_load_2d(smem + L.a_off + (b * n_kb + kb) * kFATileBytes, &map_users, a_full, kb * kFKBlock,
+                          (up * 2 + b) * kFBlockM, kEvictFirst);   // n_users are zero-filled by TMA
+        }
+        __syncwarp();
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
           const uint32_t par = it & 1, use = it >> 1;
           mbar_wait(bias_empty + par, (use & 1) ^ 1);
-          mbar_arrive_expect_tx(bias_full + par, kFBiasBytes);
-          bulk_load_1d(smem + L.bias_off + par * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
-                       kFBiasBytes, bias_full + par);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bias_full + par, kFBiasBytes);
+            bulk_load_1d(smem + L.bias_off + par * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
+                         kFBiasBytes, bias_full + par);
+          }
+          __syncwarp();
           for (int kb = 0; kb < n_kb; ++kb) {
             const uint32_t s = fill % p.n_stages;
             mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(b_full + s, kFBTileBytes);
-            tma_load_2d(smem + L.b_off + s * kFBTileBytes, &map_items, b_full + s, kb * kFKBlock, t * kFBlockN,
-                        kEvictLast);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(b_full + s, kFBTileBytes);
+              tma_load_2d(smem + L.b_off + s * kFBTileBytes, &map_items, b_full + s, kb * kFKBlock, t * kFBlockN,
+                          kEvictLast);
+            }
+            __syncwarp();
             ++fill;
           }
         }
@@ -284,7 +293,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and polls the barriers; one elected lane issues.  Issuing
+    // from inside `if (lane == 0)` makes ptxas wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (~17
+    // instructions per MMA) because it cannot prove the operands uniform.
+    {
       constexpr uint32_t idesc = umma_idesc_f16_f32(kFBlockM, kFBlockN);
       uint32_t fill = 0, witer = 0, it = 0;
       const uint32_t a_base = smem_u32(smem + L.a_off);
@@ -306,21 +318,26 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
             mbar_wait(b_full + s, (fill / p.n_stages) & 1);
             tcgen05_fence_after();
             const uint64_t db = umma_desc_k_major_sw128(b_base + s * kFBTileBytes);
+            if (elect_one()) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
-              const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
-              const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
+              for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
+                const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
+                const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
 #pragma unroll
-              for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
-                umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
+                for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
+                  umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
+              }
+              umma_commit(b_empty + s);
             }
+            __syncwarp();
             accumulate = 1;
-            umma_commit(b_empty + s);
             ++fill;
           }
-          umma_commit(tmem_full + par);
+          if (elect_one()) umma_commit(tmem_full + par);
+          __syncwarp();
         }
-        umma_commit(a_empty);
+        if (elect_one()) umma_commit(a_empty);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

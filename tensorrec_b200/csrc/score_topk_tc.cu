@@ -200,7 +200,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
-    if (lane == 0) {
+    {   // warp-uniform control flow, one elected lane issues (see the MMA warp)
       uint32_t fill = 0;   // B stages filled so far
       uint32_t witer = 0;  // non-empty work items so far
       uint32_t it = 0;     // tiles issued so far
@@ -211,24 +211,33 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
         mbar_wait(a_empty, (witer & 1) ^ 1);  // the MMAs of the previous work item no longer read A
-        mbar_arrive_expect_tx(a_full, n_kb2 * kATileBytes);
-        for (int kb = 0; kb < n_kb2; ++kb)
-          tma_load_2d(smem + L.a_off + kb * kATileBytes, &map_users, a_full, kb * kKBlock, ub * kBlockM,
-                      kEvictFirst);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full, n_kb2 * kATileBytes);
+          for (int kb = 0; kb < n_kb2; ++kb)
+            tma_load_2d(smem + L.a_off + kb * kATileBytes, &map_users, a_full, kb * kKBlock, ub * kBlockM,
+                        kEvictFirst);
+        }
+        __syncwarp();
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
           // {item scale, item bias} of this tile for the epilogue group that will drain it
           const uint32_t use = it >> 1, slot = (it & 1) * 2 + (use & 1);
           mbar_wait(meta_empty + slot, ((use >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(meta_full + slot, kMetaBytes);
-          bulk_load_1d(smem + L.meta_off + slot * kMetaBytes, p.item_meta + static_cast<int64_t>(t) * kBlockN,
-                       kMetaBytes, meta_full + slot);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(meta_full + slot, kMetaBytes);
+            bulk_load_1d(smem + L.meta_off + slot * kMetaBytes, p.item_meta + static_cast<int64_t>(t) * kBlockN,
+                         kMetaBytes, meta_full + slot);
+          }
+          __syncwarp();
           for (int kb = 0; kb < n_kb2; ++kb) {
             const uint32_t s = fill % p.n_stages;
             mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(b_full + s, kBTileBytes);
-            tma_load_2d(smem + L.b_off + s * kBTileBytes, &map_items, b_full + s, kb * kKBlock, t * kBlockN,
-                        kEvictLast);  // the item operand is re-read by every user block: keep it in L2
+            if (elect_one()) {
+              mbar_arrive_expect_tx(b_full + s, kBTileBytes);
+              tma_load_2d(smem + L.b_off + s * kBTileBytes, &map_items, b_full + s, kb * kKBlock, t * kBlockN,
+                          kEvictLast);  // the item operand is re-read by every user block: keep it in L2
+            }
+            __syncwarp();
             ++fill;
           }
         }
@@ -236,7 +245,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and polls the barriers; one elected lane issues.  Issuing
+    // from inside `if (lane == 0)` makes ptxas wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (~17
+    // instructions per MMA) because it cannot prove the operands uniform.
+    {
       constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, kBlockN);
       uint32_t fill = 0, witer = 0, it = 0;  // it = accumulator tiles produced so far
       const uint32_t a_base = smem_u32(smem + L.a_off);
@@ -263,23 +275,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
             const int kb = b_is_hi ? kb2 : kb2 - p.n_kblocks;
             // B hi block: A_hi[kb] x B and A_lo[kb] x B ;  B lo block: A_hi[kb] x B
             const int n_a = b_is_hi ? 2 : 1;
-            for (int a = 0; a < n_a; ++a) {
-              const uint32_t a_addr = a_base + (a == 0 ? kb : p.n_kblocks + kb) * kATileBytes;
-              const uint64_t da = umma_desc_k_major_sw128(a_addr);
-              const uint64_t db = umma_desc_k_major_sw128(b_addr);
+            if (elect_one()) {
+              for (int a = 0; a < n_a; ++a) {
+                const uint32_t a_addr = a_base + (a == 0 ? kb : p.n_kblocks + kb) * kATileBytes;
+                const uint64_t da = umma_desc_k_major_sw128(a_addr);
+                const uint64_t db = umma_desc_k_major_sw128(b_addr);
 #pragma unroll
-              for (int ks = 0; ks < kKBlock / kUmmaK; ++ks) {
-                // advancing 16 fp16 (32 bytes) inside the 128-byte swizzle atom = +2 in the address field
-                umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate);
-                accumulate = 1;
+                for (int ks = 0; ks < kKBlock / kUmmaK; ++ks) {
+                  // advancing 16 fp16 (32 bytes) inside the 128-byte swizzle atom = +2 in the address field
+                  umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc,
+                              (accumulate | static_cast<uint32_t>(a > 0 || ks > 0)));
+                }
               }
+              umma_commit(b_empty + s);  // stage reusable once these MMAs have read it
             }
-            umma_commit(b_empty + s);  // stage reusable once these MMAs have read it
+            __syncwarp();
+            accumulate = 1;
             ++fill;
           }
-          umma_commit(tmem_full + buf);  // accumulator complete
+          if (elect_one()) umma_commit(tmem_full + buf);  // accumulator complete
+          __syncwarp();
         }
-        umma_commit(a_empty);
+        if (elect_one()) umma_commit(a_empty);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
