@@ -173,33 +173,42 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   __syncwarp();
 }
 
-// 16 columns of one user row per lane: filter on v = acc + bias * inv_c.  The common case (no lane of the warp has a
-// column above its threshold) costs one vote and one uniform branch; otherwise the hitting lanes append their
-// survivors (with the approximate score) and rows whose buffer passed half full are compacted by the whole warp.
-__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
-                                          float inv_c, float ubias, float& tau, float& theta, float& drop_max,
-                                          float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
-  float v[16];
+// 32 columns of one user row per lane: filter on v = acc + bias * inv_c (computed in place).  The common case (no lane
+// of the warp has a column above its threshold) costs one vote and one uniform branch per 32 columns; otherwise the
+// hitting lanes append their survivors with the approximate score a = v * c + ub, and rows whose buffer passed half
+// full are compacted by the whole warp.  A buffer can only run full inside one chunk when more than 16 of its 32
+// columns pass (the very first chunk of a sweep, adversarial orderings): the surplus is dropped and remembered in
+// drop_max, which the final certificate accounts for.
+__device__ __forceinline__ void filter_32(uint32_t (&r)[32], uint32_t bias_addr, int32_t id_base, float c, float inv_c,
+                                          float ubias, float& tau, float& theta, float& drop_max, float m3,
+                                          uint32_t buf_row_addr, int& cnt, int lane, int k) {
   float vmax = -__int_as_float(0x7f800000);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const float4 b = f_lds128(bias_addr + q * 16);
-    v[4 * q + 0] = fmaf(b.x, inv_c, __uint_as_float(acc[4 * q + 0]));
-    v[4 * q + 1] = fmaf(b.y, inv_c, __uint_as_float(acc[4 * q + 1]));
-    v[4 * q + 2] = fmaf(b.z, inv_c, __uint_as_float(acc[4 * q + 2]));
-    v[4 * q + 3] = fmaf(b.w, inv_c, __uint_as_float(acc[4 * q + 3]));
-    vmax = fmaxf(vmax, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
+    const float v0 = fmaf(b.x, inv_c, __uint_as_float(r[4 * q + 0]));
+    const float v1 = fmaf(b.y, inv_c, __uint_as_float(r[4 * q + 1]));
+    const float v2 = fmaf(b.z, inv_c, __uint_as_float(r[4 * q + 2]));
+    const float v3 = fmaf(b.w, inv_c, __uint_as_float(r[4 * q + 3]));
+    r[4 * q + 0] = __float_as_uint(v0);
+    r[4 * q + 1] = __float_as_uint(v1);
+    r[4 * q + 2] = __float_as_uint(v2);
+    r[4 * q + 3] = __float_as_uint(v3);
+    vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
   }
   const bool hit = vmax > tau;
   if (__any_sync(0xffffffffu, hit)) {
     if (hit) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (v[j] > tau) {
-          const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + f_lds32(bias_addr + j * 4);   // approximate score
-          if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
+      for (int j = 0; j < 32; ++j) {
+        const float v = __uint_as_float(r[j]);
+        if (v > tau) {
+          const float a = fmaf(v, c, ubias);   // approximate score (v * c = acc * c + bias_j up to rounding)
+          if (cnt < kBufEntries) {
             f_sts64(buf_row_addr + cnt * 8, a, id_base + j);
             cnt += 1;
+          } else {
+            drop_max = fmaxf(drop_max, a);
           }
         }
       }
@@ -410,18 +419,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 #pragma unroll 1
         for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
-                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
-          }
+          filter_32(ra, bias_base + ch * 32 * 4, id0 + ch * 32, c, inv_c, ubias, tau, theta, drop_max, m3,
+                    buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
-                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
-          }
+          filter_32(rb, bias_base + (ch + 1) * 32 * 4, id0 + (ch + 1) * 32, c, inv_c, ubias, tau, theta, drop_max,
+                    m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
         }
       drained:
@@ -715,16 +718,12 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
 #pragma unroll 1
         for (int ch = 0; ch < 4; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
-                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          filter_32(ra, bias_base + ch * 32 * 4, id0 + ch * 32, c, inv_c, ubias, tau, theta, drop_max, m3,
+                    buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
-                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          filter_32(rb, bias_base + (ch + 1) * 32 * 4, id0 + (ch + 1) * 32, c, inv_c, ubias, tau, theta, drop_max,
+                    m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
         }
         if (theta > theta_before) f_sts64(theta_mine, theta, epoch);   // publish the tightened threshold
