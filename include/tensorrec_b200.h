@@ -161,8 +161,8 @@ int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const 
  *   trk_pack_item_bias     bias padded with -inf to n_padded (multiple of 256) entries; stats[2] = max |bias|
  * Filter outputs, two lists per (user, split): cand_* [n_users, n_splits, 2, 16] (approximate score, global id;
  * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits, 2].
- * The kernel runs as clusters of two CTAs (tcgen05 cta_group::2, M = 256); TRK_FILTER_FORM=single selects the
- * one-CTA form.
+ * Two launch forms: one CTA per 256 users (default) or, with TRK_FILTER_FORM=pair, clusters of two CTAs driving
+ * tcgen05 cta_group::2 MMAs (M = 256 across two SMs).
  * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_filter_max_k(); n_components <= 128 for the rescoring.
  * ---------------------------------------------------------------------------------------------------- */
 int trk_score_filter_max_k(void);

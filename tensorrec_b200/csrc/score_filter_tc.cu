@@ -173,42 +173,33 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   __syncwarp();
 }
 
-// 32 columns of one user row per lane: filter on v = acc + bias * inv_c (computed in place).  The common case (no lane
-// of the warp has a column above its threshold) costs one vote and one uniform branch per 32 columns; otherwise the
-// hitting lanes append their survivors with the approximate score a = v * c + ub, and rows whose buffer passed half
-// full are compacted by the whole warp.  A buffer can only run full inside one chunk when more than 16 of its 32
-// columns pass (the very first chunk of a sweep, adversarial orderings): the surplus is dropped and remembered in
-// drop_max, which the final certificate accounts for.
-__device__ __forceinline__ void filter_32(uint32_t (&r)[32], uint32_t bias_addr, int32_t id_base, float c, float inv_c,
-                                          float ubias, float& tau, float& theta, float& drop_max, float m3,
-                                          uint32_t buf_row_addr, int& cnt, int lane, int k) {
+// 16 columns of one user row per lane: filter on v = acc + bias * inv_c.  The common case (no lane of the warp has a
+// column above its threshold) costs one vote and one uniform branch; otherwise the hitting lanes append their
+// survivors (with the approximate score) and rows whose buffer passed half full are compacted by the whole warp.
+__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
+                                          float inv_c, float ubias, float& tau, float& theta, float& drop_max,
+                                          float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+  float v[16];
   float vmax = -__int_as_float(0x7f800000);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < 4; ++q) {
     const float4 b = f_lds128(bias_addr + q * 16);
-    const float v0 = fmaf(b.x, inv_c, __uint_as_float(r[4 * q + 0]));
-    const float v1 = fmaf(b.y, inv_c, __uint_as_float(r[4 * q + 1]));
-    const float v2 = fmaf(b.z, inv_c, __uint_as_float(r[4 * q + 2]));
-    const float v3 = fmaf(b.w, inv_c, __uint_as_float(r[4 * q + 3]));
-    r[4 * q + 0] = __float_as_uint(v0);
-    r[4 * q + 1] = __float_as_uint(v1);
-    r[4 * q + 2] = __float_as_uint(v2);
-    r[4 * q + 3] = __float_as_uint(v3);
-    vmax = fmaxf(vmax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
+    v[4 * q + 0] = fmaf(b.x, inv_c, __uint_as_float(acc[4 * q + 0]));
+    v[4 * q + 1] = fmaf(b.y, inv_c, __uint_as_float(acc[4 * q + 1]));
+    v[4 * q + 2] = fmaf(b.z, inv_c, __uint_as_float(acc[4 * q + 2]));
+    v[4 * q + 3] = fmaf(b.w, inv_c, __uint_as_float(acc[4 * q + 3]));
+    vmax = fmaxf(vmax, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
   }
   const bool hit = vmax > tau;
   if (__any_sync(0xffffffffu, hit)) {
     if (hit) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = __uint_as_float(r[j]);
-        if (v > tau) {
-          const float a = fmaf(v, c, ubias);   // approximate score (v * c = acc * c + bias_j up to rounding)
-          if (cnt < kBufEntries) {
+      for (int j = 0; j < 16; ++j) {
+        if (v[j] > tau) {
+          const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + f_lds32(bias_addr + j * 4);   // approximate score
+          if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
             f_sts64(buf_row_addr + cnt * 8, a, id_base + j);
             cnt += 1;
-          } else {
-            drop_max = fmaxf(drop_max, a);
           }
         }
       }
@@ -220,6 +211,33 @@ __device__ __forceinline__ void filter_32(uint32_t (&r)[32], uint32_t bias_addr,
       need &= need - 1;
       compact_row(buf_row_addr, lane, src, k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
     }
+  }
+}
+
+// 32-column front end: one vote per chunk.  The fast path only needs the chunk maximum of v (32 FFMA + 16 FMNMX3 with
+// no control dependency in between); when some lane has a hit the two 16-column halves go through filter_16, which
+// recomputes v for the hitting lanes (rare) and keeps the buffer invariant cnt <= 16 per half.
+__device__ __forceinline__ void filter_32(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
+                                          float inv_c, float ubias, float& tau, float& theta, float& drop_max,
+                                          float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+  float m0 = -__int_as_float(0x7f800000), m1 = m0;
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    const float4 b0 = f_lds128(bias_addr + q * 16);
+    const float4 b1 = f_lds128(bias_addr + q * 16 + 16);
+    m0 = fmaxf(m0, fmaxf(fmaxf(fmaf(b0.x, inv_c, __uint_as_float(acc[4 * q + 0])),
+                               fmaf(b0.y, inv_c, __uint_as_float(acc[4 * q + 1]))),
+                         fmaxf(fmaf(b0.z, inv_c, __uint_as_float(acc[4 * q + 2])),
+                               fmaf(b0.w, inv_c, __uint_as_float(acc[4 * q + 3])))));
+    m1 = fmaxf(m1, fmaxf(fmaxf(fmaf(b1.x, inv_c, __uint_as_float(acc[4 * q + 4])),
+                               fmaf(b1.y, inv_c, __uint_as_float(acc[4 * q + 5]))),
+                         fmaxf(fmaf(b1.z, inv_c, __uint_as_float(acc[4 * q + 6])),
+                               fmaf(b1.w, inv_c, __uint_as_float(acc[4 * q + 7])))));
+  }
+  if (__any_sync(0xffffffffu, fmaxf(m0, m1) > tau)) {
+    filter_16(acc, bias_addr, id_base, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, k);
+    filter_16(acc + 16, bias_addr + 64, id_base + 16, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
+              lane, k);
   }
 }
 
@@ -948,8 +966,11 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     const char* dbg = getenv("TRK_FILTER_DEBUG");
     p.debug_mode = dbg != nullptr ? atoi(dbg) : 0;
   }
-  const char* form = getenv("TRK_FILTER_FORM");        // "single" = one CTA per 256 users; default = CTA pairs
-  const bool pair_form = !(form != nullptr && form[0] == 's');
+  // Form: "single" (default) = one CTA per 256 users, one candidate list per row; "pair" = clusters of two CTAs
+  // (tcgen05 cta_group::2).  Measured at 1M x 1M x d128 (scripts/filter_probe.py): the pair form has the faster mainloop
+  // (196 ms vs 227 ms without epilogue) but keeps two lists per row, and the epilogue is what bounds both: 350 ms vs 311 ms.
+  const char* form = getenv("TRK_FILTER_FORM");
+  const bool pair_form = form != nullptr && form[0] == 'p';
 
   CUtensorMap map_users, map_items;
   int rc = make_hi_map(&map_users, user_split, n_users, 2 * d_pad, d_pad, kFBlockM);

@@ -56,19 +56,21 @@ struct TcParams {
   int32_t* cand_item;
   float* dense_out;         // dense mode output
   int64_t dense_stride;
+  int32_t tma_store;        // dense mode: 1 = rows are 16-byte aligned, the epilogue stores through TMA
 };
 
 // shared-memory carve-up (offsets from a 1024-byte aligned base)
 struct SmemLayout {
   uint32_t a_off, b_off, list_score_off, list_item_off, meta_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout make_layout(int n_kblocks, int n_stages, int k) {
+constexpr uint32_t kStoreTileBytes = 32 * 32 * 4;   // one warp's 32 rows x 32 columns of fp32 scores
+__host__ __device__ inline SmemLayout make_layout(int n_kblocks, int n_stages, int k, bool dense_staging = false) {
   SmemLayout L;
   L.a_off = 0;
   L.b_off = L.a_off + 2u * n_kblocks * kATileBytes;
   L.list_score_off = L.b_off + static_cast<uint32_t>(n_stages) * kBTileBytes;
-  L.list_item_off = L.list_score_off + 2u * k * kBlockM * 4u;
-  L.meta_off = L.list_item_off + 2u * k * kBlockM * 4u;
+  L.list_item_off = L.list_score_off + (dense_staging ? 16u * kStoreTileBytes : 2u * k * kBlockM * 4u);
+  L.meta_off = L.list_item_off + (dense_staging ? 0u : 2u * k * kBlockM * 4u);
   L.bar_off = L.meta_off + 4u * kMetaBytes;      // 2 groups x 2 slots, filled by the TMA warp
   L.total = L.bar_off + 512u;
   return L;
@@ -149,14 +151,39 @@ __device__ __forceinline__ void process_chunk(uint32_t (&r)[32], int c, int t, i
   }
 }
 
+// Dense mode, TMA path: the warp's 32 rows x 32 columns go to a 128B-swizzled staging tile in shared memory and
+// leave as ONE cp.async.bulk.tensor store (full 128-byte lines per row, rows / columns beyond the matrix clipped by the
+// tensor map).  Direct stores from the row-per-thread layout write 16 bytes per lane to 32 different rows.
+__device__ __forceinline__ void store_chunk_tma(const uint32_t (&r)[32], uint32_t stage_addr, int lane,
+                                                const CUtensorMap* map_out, int32_t col0, int32_t row0) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the buffer used two chunks ago
+  __syncwarp();
+#pragma unroll
+  for (int c16 = 0; c16 < 8; ++c16) {
+    const uint32_t addr = stage_addr + lane * 128 + ((c16 ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * c16]), "r"(r[4 * c16 + 1]),
+                 "r"(r[4 * c16 + 2]), "r"(r[4 * c16 + 3])
+                 : "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map_out)),
+                 "r"(stage_addr), "r"(col0), "r"(row0)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 template <bool kDense>
 __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
-                const TcParams p) {
+                const __grid_constant__ CUtensorMap map_out, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need a 1024-byte aligned base
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const SmemLayout L = make_layout(p.n_kblocks, p.n_stages, kDense ? 0 : p.k);
+  const SmemLayout L = make_layout(p.n_kblocks, p.n_stages, kDense ? 0 : p.k, kDense && p.tma_store != 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
@@ -309,6 +336,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     int32_t* li = reinterpret_cast<int32_t*>(smem + L.list_item_off) + group * (kDense ? 0 : p.k) * kBlockM + row;
     const float kNegInf = -__int_as_float(0x7f800000);
     uint32_t it = 0;
+    uint32_t n_stored = 0;   // dense TMA path: chunks stored by this warp (selects the staging buffer)
+    const uint32_t stage_base = smem_u32(smem + L.list_score_off) + static_cast<uint32_t>(warp - 4) * 2u * kStoreTileBytes;
 
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ub = static_cast<int>(w % p.n_user_blocks);
@@ -342,10 +371,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
 #pragma unroll 1
         for (int c = 0; c < kBlockN / 32; c += 2) {
           tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rb);   // in flight while chunk c is scored
-          process_chunk<kDense>(ra, c, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
+          if (kDense && p.tma_store) {
+            score_chunk(ra, meta_base + c * 32 * 8, su, ubias);
+            store_chunk_tma(ra, stage_base + (n_stored & 1) * kStoreTileBytes, lane, &map_out, t * kBlockN + c * 32,
+                            ub * kBlockM + quarter * 32);
+            ++n_stored;
+          } else {
+            process_chunk<kDense>(ra, c, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
+          }
           tmem_ld_wait();
           if (c + 2 < kBlockN / 32) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
-          process_chunk<kDense>(rb, c + 1, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
+          if (kDense && p.tma_store) {
+            score_chunk(rb, meta_base + (c + 1) * 32 * 8, su, ubias);
+            store_chunk_tma(rb, stage_base + (n_stored & 1) * kStoreTileBytes, lane, &map_out,
+                            t * kBlockN + (c + 1) * 32, ub * kBlockM + quarter * 32);
+            ++n_stored;
+          } else {
+            process_chunk<kDense>(rb, c + 1, t, id0, meta_base, su, ubias, thr, ls, li, p, u, u_ok);
+          }
           tmem_ld_wait();
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -384,6 +427,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   }
 
   // ---- teardown ----
+  if (kDense && p.tma_store && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -437,9 +481,9 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int d_pad
 
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
-int pick_stages(int n_kblocks, int k) {
+int pick_stages(int n_kblocks, int k, bool dense_staging) {
   for (int s = kMaxStages; s >= 2; --s)
-    if (make_layout(n_kblocks, s, k).total + 1024 <= kSmemLimit) return s;
+    if (make_layout(n_kblocks, s, k, dense_staging).total + 1024 <= kSmemLimit) return s;
   return 0;
 }
 
@@ -493,7 +537,8 @@ static int launch_tc(const void* user_split, const float* user_scale, const floa
   p.cand_item = cand_item;
   p.dense_out = dense_out;
   p.dense_stride = dense_stride;
-  p.n_stages = pick_stages(p.n_kblocks, p.k);
+  p.tma_store = (kDense && dense_stride % 4 == 0 && reinterpret_cast<uintptr_t>(dense_out) % 16 == 0) ? 1 : 0;
+  p.n_stages = pick_stages(p.n_kblocks, p.k, p.tma_store != 0);
   TRK_CHECK_ARG(p.n_stages >= 2, "score_tc: shared memory budget exceeded (d_pad=%d k=%d)", d_pad, k);
 
   CUtensorMap map_users, map_items;
@@ -502,12 +547,27 @@ static int launch_tc(const void* user_split, const float* user_scale, const floa
   rc = make_operand_map(&map_items, item_split, n_items, d_pad, kBlockN);
   if (rc != TRK_OK) return rc;
 
-  const uint32_t smem_bytes = make_layout(p.n_kblocks, p.n_stages, p.k).total + 1024;
+  CUtensorMap map_out = map_items;   // placeholder when the TMA store path is off
+  if (p.tma_store) {
+    EncodeTiledFn encode = get_encode_fn();
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(n_items), static_cast<cuuint64_t>(n_users)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(dense_stride) * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t elem_strides[2] = {1, 1};
+    const CUresult r = encode(&map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dense_out, dims, strides, box,
+                              elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d", static_cast<int>(r));
+      return TRK_ERR_CUDA;
+    }
+  }
+  const uint32_t smem_bytes = make_layout(p.n_kblocks, p.n_stages, p.k, p.tma_store != 0).total + 1024;
   auto kernel = score_tc_kernel<kDense>;
   TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * n_splits;
   const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
-  kernel<<<grid, kTcThreads, smem_bytes, stream>>>(map_users, map_items, p);
+  kernel<<<grid, kTcThreads, smem_bytes, stream>>>(map_users, map_items, map_out, p);
   TRK_CHECK_LAUNCH();
   return TRK_OK;
 }

@@ -435,3 +435,24 @@ def test_filter_candidates_respect_the_error_bound(K):
         assert np.all(np.abs(cs[u][real] - scores[u, ci[u][real]]) <= m[u])
         assert set(exp_i[u]) <= set(ci[u][real])
         assert real.sum() <= 64
+
+
+@pytest.mark.parametrize('form', ['single', 'pair'])
+@pytest.mark.parametrize('U,I,d,k,integer', [(700, 9000, 128, 10, False), (300, 1500, 64, 5, True), (257, 513, 100, 12, False)])
+def test_filter_launch_forms(K, monkeypatch, form, U, I, d, k, integer):
+    """Both launch forms of the filter kernel (one CTA per 256 users / tcgen05 cta_group::2 CTA pairs) give the
+    reference top-k."""
+    monkeypatch.setenv('TRK_FILTER_FORM', form)
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, integer, seed=U + I, regime='tag' if integer else 'indicator')
+    scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k)
+    if integer:
+        assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
+    else:
+        rows = np.arange(U)[:, None]
+        model = oracle.OracleModel([wu], wi, bu, bi)
+        tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + 2e-6
+        assert np.all(np.abs(got_s - scores[rows, got_i]) <= tol[rows, got_i])
+        assert (got_i != exp_i).mean() < 0.01
+        assert info['fallback_rows'] <= U // 20
