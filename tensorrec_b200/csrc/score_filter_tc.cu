@@ -214,33 +214,6 @@ __device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_add
   }
 }
 
-// 32-column front end: one vote per chunk.  The fast path only needs the chunk maximum of v (32 FFMA + 16 FMNMX3 with
-// no control dependency in between); when some lane has a hit the two 16-column halves go through filter_16, which
-// recomputes v for the hitting lanes (rare) and keeps the buffer invariant cnt <= 16 per half.
-__device__ __forceinline__ void filter_32(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
-                                          float inv_c, float ubias, float& tau, float& theta, float& drop_max,
-                                          float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
-  float m0 = -__int_as_float(0x7f800000), m1 = m0;
-#pragma unroll
-  for (int q = 0; q < 8; q += 2) {
-    const float4 b0 = f_lds128(bias_addr + q * 16);
-    const float4 b1 = f_lds128(bias_addr + q * 16 + 16);
-    m0 = fmaxf(m0, fmaxf(fmaxf(fmaf(b0.x, inv_c, __uint_as_float(acc[4 * q + 0])),
-                               fmaf(b0.y, inv_c, __uint_as_float(acc[4 * q + 1]))),
-                         fmaxf(fmaf(b0.z, inv_c, __uint_as_float(acc[4 * q + 2])),
-                               fmaf(b0.w, inv_c, __uint_as_float(acc[4 * q + 3])))));
-    m1 = fmaxf(m1, fmaxf(fmaxf(fmaf(b1.x, inv_c, __uint_as_float(acc[4 * q + 4])),
-                               fmaf(b1.y, inv_c, __uint_as_float(acc[4 * q + 5]))),
-                         fmaxf(fmaf(b1.z, inv_c, __uint_as_float(acc[4 * q + 6])),
-                               fmaf(b1.w, inv_c, __uint_as_float(acc[4 * q + 7])))));
-  }
-  if (__any_sync(0xffffffffu, fmaxf(m0, m1) > tau)) {
-    filter_16(acc, bias_addr, id_base, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, k);
-    filter_16(acc + 16, bias_addr + 64, id_base + 16, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
-              lane, k);
-  }
-}
-
 __global__ void __launch_bounds__(kFThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                     const FilterParams p) {
@@ -437,12 +410,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 #pragma unroll 1
         for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
-          filter_32(ra, bias_base + ch * 32 * 4, id0 + ch * 32, c, inv_c, ubias, tau, theta, drop_max, m3,
-                    buf_row_addr, cnt, lane, p.k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
+                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          filter_32(rb, bias_base + (ch + 1) * 32 * 4, id0 + (ch + 1) * 32, c, inv_c, ubias, tau, theta, drop_max,
-                    m3, buf_row_addr, cnt, lane, p.k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
+                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
         }
       drained:
@@ -736,12 +713,16 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
 #pragma unroll 1
         for (int ch = 0; ch < 4; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
-          filter_32(ra, bias_base + ch * 32 * 4, id0 + ch * 32, c, inv_c, ubias, tau, theta, drop_max, m3,
-                    buf_row_addr, cnt, lane, p.k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
+                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          filter_32(rb, bias_base + (ch + 1) * 32 * 4, id0 + (ch + 1) * 32, c, inv_c, ubias, tau, theta, drop_max,
-                    m3, buf_row_addr, cnt, lane, p.k);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
+                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
         }
         if (theta > theta_before) f_sts64(theta_mine, theta, epoch);   // publish the tightened threshold
