@@ -184,6 +184,15 @@ class ClockSampler(object):
                 'power_w_max': float(max(power)), 'samples': len(sm)}
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes (read + write) of one launch of the dominant kernel at the bench workload, from the committed ncu
+    capture (profiles/ncu_traffic.json, written by scripts/ncu_summary.py runs); None if not captured."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get(kernel_key)
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -360,9 +369,10 @@ def run_b200(args):
     flops = 2.0 * n_users * n_local * d                        # algorithmic flops of one fused launch (this rank)
     achieved = flops / (fused_ms * 1e-3) / 1e12
     peak = peaks['tflops_sustained']
-    # K1 (users) algorithmic bytes: nnz*8 + (R+1)*4 + D*d*4 + R*(2*d_pad*2 + 4)   (D = distinct columns)
+    # K1 (users) algorithmic bytes: nnz*8 + (R+1)*4 + D*d*4 + R*(2*d_pad*2 + 4) [+ R*d*4]  (D = distinct columns)
     distinct = int(np.unique(uf.indices).shape[0])
-    k1_bytes = uf.nnz * 8 + (n_users + 1) * 4 + distinct * d * 4 + n_users * (2 * d_pad * 2 + 4)
+    k1_bytes = (uf.nnz * 8 + (n_users + 1) * 4 + distinct * d * 4 + n_users * (2 * d_pad * 2 + 4)
+                + (n_users * d * 4 if use_filter else 0))      # the filter path also writes the fp32 representation
     k1_gbs = k1_bytes / (k1u_ms * 1e-3) / 1e9
 
     cores = os.cpu_count() or 1
@@ -388,7 +398,9 @@ def run_b200(args):
         'gpu_launches': launches_per_step * args.steps,
         'roofline': {'kernel': ('score_filter_kernel (trk_score_filter_f16)' if use_filter
                                 else 'score_tc_kernel<topk> (trk_score_topk_f16x3)'), 'bound': 'tensor',
-                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'traffic': ncu_traffic('score_filter_kernel@%dx%dx%d' % (n_users, n_local, d)) if use_filter
+                     else ncu_traffic('score_tc_kernel@%dx%dx%d' % (n_users, n_local, d)),
                      'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'ms_per_launch': fused_ms,
                      'issued_tflops': (1 if use_filter else 3) * achieved,
                      'issued_frac': (1 if use_filter else 3) * achieved / peak, 'share_of_step': fused_ms / ms_step},
