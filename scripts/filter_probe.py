@@ -48,8 +48,13 @@ pairs = A.users * float(A.items)
 os.environ['TRK_FILTER_FORM'] = 'single'
 ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
 print('filter single-CTA form: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+for mode in ('1', '2', '3'):
+    os.environ['TRK_FILTER_DEBUG'] = mode
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
+    print('single form debug=%s: %.2f ms' % (mode, ms))
+os.environ['TRK_FILTER_DEBUG'] = '0'
 os.environ['TRK_FILTER_FORM'] = 'pair'
-for mode in ('0', '1', '2'):
+for mode in (('0', '1', '2') if os.environ.get('PROBE_PAIR') else ()):
     os.environ['TRK_FILTER_DEBUG'] = mode
     ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
     print('filter debug=%s: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (mode, ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))

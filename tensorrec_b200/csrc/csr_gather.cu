@@ -172,15 +172,18 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
 #pragma unroll
         for (int w = 0; w < W; ++w) acc[j][w] = 0.0f;
 
-      int p = a;
-      // four gathers in flight, FMAs retired in storage order
-      for (; p + 4 <= b; p += 4) {
+      // batches of four entries: all (up to four) gathers of a batch are issued before the first FMA, also for rows
+      // with fewer than four entries left (a scalar tail would serialise one memory latency per entry); FMAs retire
+      // in storage order
+      for (int p = a; p < b; p += 4) {
+        const int n = min(4, b - p);
         int c[4];
         float v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          c[q] = staged ? s_col[p + q - p0] : __ldg(col + p + q);
-          v[q] = staged ? s_val[p + q - p0] : __ldg(val + p + q);
+          const int pq = p + (q < n ? q : 0);
+          c[q] = staged ? s_col[pq - p0] : __ldg(col + pq);
+          v[q] = staged ? s_val[pq - p0] : __ldg(val + pq);
         }
         float wv[4][CH][W];
 #pragma unroll
@@ -189,7 +192,7 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             const int e0 = (lane + G * j) * W;
-            if (e0 < d) {
+            if (q < n && e0 < d) {
               if constexpr (VEC) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + e0));
                 wv[q][j][0] = t.x; wv[q][j][1] = t.y; wv[q][j][2] = t.z; wv[q][j][3] = t.w;
@@ -204,30 +207,12 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
+          if (q < n) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
+            for (int j = 0; j < CH; ++j)
 #pragma unroll
-            for (int w = 0; w < W; ++w) acc[j][w] = fmaf(v[q], wv[q][j][w], acc[j][w]);
-      }
-      for (; p < b; ++p) {
-        const int c = staged ? s_col[p - p0] : __ldg(col + p);
-        const float v = staged ? s_val[p - p0] : __ldg(val + p);
-        const float* wrow = weights + static_cast<int64_t>(c) * d;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int e0 = (lane + G * j) * W;
-          if (e0 < d) {
-            if constexpr (VEC) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + e0));
-              acc[j][0] = fmaf(v, t.x, acc[j][0]);
-              acc[j][1] = fmaf(v, t.y, acc[j][1]);
-              acc[j][2] = fmaf(v, t.z, acc[j][2]);
-              acc[j][3] = fmaf(v, t.w, acc[j][3]);
-            } else {
-              acc[j][0] = fmaf(v, __ldg(wrow + e0), acc[j][0]);
-            }
+              for (int w = 0; w < W; ++w) acc[j][w] = fmaf(v[q], wv[q][j][w], acc[j][w]);
           }
-        }
       }
       row_epilogue<G, CH, VEC>(acc, lane, r0 + rr, active, d, n_normalize, out_f32, out_split, d_pad, out_scale);
     }

@@ -67,7 +67,8 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
-  int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain
+  int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
+                               // 3 = full epilogue but no MMA issued after the first two tiles (stale accumulators)
   float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
   float* row_theta;            // [n_users, n_splits, 2] final admission threshold
@@ -336,6 +337,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
               for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
                 const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
                 const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
+                if (p.debug_mode == 3 && t > t0 + 1) continue;   // timing experiment: epilogue without MMA work
 #pragma unroll
                 for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
                   umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
