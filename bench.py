@@ -257,28 +257,19 @@ def run_b200(args):
         users = kernels.SideOperands(u32, us, usc, ub, n_users, d, d_pad)
         items = kernels.SideOperands(i32, its, isc, ib, n_local, d, d_pad)
         if use_filter:
-            stats = torch.zeros((3,), dtype=torch.float32, device=dev)
             user_norm = kernels.operand_stats(us, usc, d_pad)
-            kernels.operand_stats(its, isc, d_pad, want_norm=False, stats=stats)
-            item_hi = kernels.rescale_hi_global(its, isc, stats, d_pad)
-            bias_pad = kernels.pack_item_bias(ib, n_local, stats, dev)
+            fitems = kernels.FilterItems(items)      # stats, bias-sorted processing order, global-scale hi, bias blocks
             if record:
                 e[2].record()
-            cs, ci, theta, flags = kernels.score_filter(us, usc, ub, user_norm, item_hi, stats, bias_pad, n_users,
+            cs, ci, theta, flags = kernels.score_filter(us, usc, ub, user_norm, fitems.hi, fitems.stats,
+                                                        fitems.bias_pad, fitems.block_max, fitems.perm, n_users,
                                                         n_local, d_pad, k, item_id_offset=lo)
             if record:
                 e[3].record()
-            ts, ti, bad = kernels.rescore_topk(u32, i32, ub, ib, ci, theta, flags, user_norm, stats, k,
+            ts, ti, bad = kernels.rescore_topk(u32, i32, ub, ib, ci, theta, flags, user_norm, fitems.stats, k,
                                                item_id_offset=lo)
-            n_bad = int(bad.sum().item())
-            info['fallback_rows'] = n_bad
-            if n_bad:      # rows whose bound could not be certified go through the exact kernel (inside the timed step)
-                idx = bad.nonzero(as_tuple=True)[0]
-                sub = kernels.SideOperands(None, us.index_select(0, idx).contiguous(), usc.index_select(0, idx),
-                                           ub.index_select(0, idx), int(idx.numel()), d, d_pad)
-                ex_s, ex_i = kernels.topk_exact(sub, items, k, item_id_offset=lo)
-                ts.index_copy_(0, idx, ex_s)
-                ti.index_copy_(0, idx, ex_i)
+            # rows whose bound could not be certified go through the exact kernel (inside the timed step)
+            info['fallback_rows'] = kernels.rerun_uncertified(users, items, bad, ts, ti, k, item_id_offset=lo)
         else:
             meta = kernels.pack_item_meta(isc, ib, n_local)
             if record:

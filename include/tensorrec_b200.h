@@ -156,9 +156,14 @@ int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const 
  *   trk_operand_stats      norm[r] = |row r|_2 (upper bound) of a split operand; stats[0] = max norm, stats[1] = max
  *                          row scale, both by atomic max (stats[3] must be zeroed by the caller; either output may be
  *                          NULL)
- *   trk_rescale_hi_global  item "hi" half re-expressed with ONE scale for the whole matrix: out_hi [rows, d_pad] f16 =
- *                          hi[r,:] * (scale[r] / stats[1])   (exact power-of-two factors)
- *   trk_pack_item_bias     bias padded with -inf to n_padded (multiple of 256) entries; stats[2] = max |bias|
+ *   trk_rescale_hi_global  item "hi" half re-expressed with ONE scale for the whole matrix and laid out in PROCESSING
+ *                          order: out_hi[p, :] (f16 [rows, d_pad]) = hi[perm[p], :] * (scale[perm[p]] / stats[1]) (exact
+ *                          power-of-two factors; perm NULL = identity)
+ *   trk_pack_item_bias     out[p] = bias[perm[p]], padded with -inf to n_padded (multiple of 256) entries; stats[2] =
+ *                          max |bias|; block_max[b] = max bias of positions [128 b, 128 b + 128)
+ * Processing order: the host sorts the items by bias (perm = stable argsort) so that the biases inside a 128-item
+ * block are nearly equal; the kernel's hot loop then bounds acc_j + bias_j / c by max_j acc_j + block_max / c and
+ * touches neither the biases nor an FFMA per score.  Candidate ids are reported in ORIGINAL numbering.
  * Filter outputs, two lists per (user, split): cand_* [n_users, n_splits, 2, 16] (approximate score, global id;
  * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits, 2].
  * Two launch forms: one CTA per 256 users (default) or, with TRK_FILTER_FORM=pair, clusters of two CTAs driving
@@ -169,15 +174,16 @@ int trk_score_filter_max_k(void);
 int trk_score_filter_list_width(void); /* candidates per list: 16 (two lists per (user, split)) */
 int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm,
                       float* stats, void* stream);
-int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
-                          void* out_hi, void* stream);
-int trk_pack_item_bias(const float* item_bias, int64_t n_items, float* out, int64_t n_items_padded, float* stats,
-                       void* stream);
+int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, const int32_t* perm,
+                          int64_t rows, int32_t d_pad, void* out_hi, void* stream);
+int trk_pack_item_bias(const float* item_bias, const int32_t* perm, int64_t n_items, float* out,
+                       int64_t n_items_padded, float* stats, float* block_max, void* stream);
 int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                          const float* user_norm, const void* item_hi_global, const float* item_stats,
-                         const float* item_bias_padded, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
-                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
-                         float* row_theta, int32_t* row_flags, void* stream);
+                         const float* item_bias_padded, const float* block_bias_max, const int32_t* item_perm,
+                         int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
+                         int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
+                         int32_t* row_flags, void* stream);
 /* item_repr holds the rows of THIS shard: global id g lives at row g - item_id_offset.  n_lists = 2 * n_splits,
  * list_width = 16.  out_flag[u] = 1 -> re-run user u through the exact kernel. */
 int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,

@@ -27,8 +27,9 @@ ib = kernels.project_biases(icsr, torch.from_numpy(bi).to(dev))
 stats = torch.zeros(3, device=dev)
 unorm = kernels.operand_stats(us, usc, d_pad)
 kernels.operand_stats(its, isc, d_pad, want_norm=False, stats=stats)
-hi = kernels.rescale_hi_global(its, isc, stats, d_pad)
-bias_pad = kernels.pack_item_bias(ib, A.items, stats, dev)
+perm = None if os.environ.get('PROBE_NO_SORT') else kernels.bias_processing_order(ib)
+hi = kernels.rescale_hi_global(its, isc, stats, d_pad, perm=perm)
+bias_pad, bmax = kernels.pack_item_bias(ib, A.items, stats, dev, perm=perm)
 meta = kernels.pack_item_meta(isc, ib, A.items)
 
 
@@ -46,22 +47,31 @@ def timeit(fn, n=3):
 
 pairs = A.users * float(A.items)
 os.environ['TRK_FILTER_FORM'] = 'single'
-ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
+ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
 print('filter single-CTA form: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
-for mode in ('1', '2', '3'):
+for vote in ('16', '32'):
+    os.environ['TRK_FILTER_VOTE'] = vote
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
+    print('single form, vote per %s columns: %.2f ms' % (vote, ms))
+    os.environ['TRK_FILTER_DEBUG'] = '4'
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
+    print('single form, vote per %s columns, nothing admitted: %.2f ms' % (vote, ms))
+    os.environ['TRK_FILTER_DEBUG'] = '0'
+os.environ.pop('TRK_FILTER_VOTE')
+for mode in ('7', '1', '2', '6'):
     os.environ['TRK_FILTER_DEBUG'] = mode
-    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
     print('single form debug=%s: %.2f ms' % (mode, ms))
 os.environ['TRK_FILTER_DEBUG'] = '0'
 os.environ['TRK_FILTER_FORM'] = 'pair'
 for mode in (('0', '1', '2') if os.environ.get('PROBE_PAIR') else ()):
     os.environ['TRK_FILTER_DEBUG'] = mode
-    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k))
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
     print('filter debug=%s: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (mode, ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
 os.environ['TRK_FILTER_DEBUG'] = '0'
 ms = timeit(lambda: kernels.score_topk(us, usc, ub, its, meta, A.users, A.items, d_pad, A.k))
 print('exact top-k (3 pass): %.2f ms  %.3e pairs/s  issued %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 6 * pairs * A.d / ms / 1e9))
-ms = timeit(lambda: kernels.rescore_topk(u32, i32, ub, ib, kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k)[1], *kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, A.users, A.items, d_pad, A.k)[2:], unorm, stats, A.k), n=1)
+ms = timeit(lambda: kernels.rescore_topk(u32, i32, ub, ib, kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k)[1], *kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k)[2:], unorm, stats, A.k), n=1)
 print('2x filter + rescore: %.2f ms' % ms)
 nu = min(A.users, 32768)
 out = torch.empty((nu, A.items), dtype=torch.float32, device=dev)

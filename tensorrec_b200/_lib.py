@@ -45,10 +45,10 @@ SIGNATURES = {
     'trk_score_filter_max_k': (ctypes.c_int, []),
     'trk_score_filter_list_width': (ctypes.c_int, []),
     'trk_operand_stats': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p, _c_p]),
-    'trk_rescale_hi_global': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p]),
-    'trk_pack_item_bias': (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p]),
-    'trk_score_filter_f16': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32, _c_i32,
-                                            _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    'trk_rescale_hi_global': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p]),
+    'trk_pack_item_bias': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p]),
+    'trk_score_filter_f16': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32,
+                                            _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
     'trk_rescore_topk_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32,
                                             _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p]),
 }

@@ -47,11 +47,11 @@ int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t,
 int score_filter_max_k();
 int score_filter_list_width();
 int operand_stats(const void*, const float*, int64_t, int32_t, float*, float*, cudaStream_t);
-int rescale_hi_global(const void*, const float*, const float*, int64_t, int32_t, void*, cudaStream_t);
-int pack_item_bias(const float*, int64_t, float*, int64_t, float*, cudaStream_t);
+int rescale_hi_global(const void*, const float*, const float*, const int32_t*, int64_t, int32_t, void*, cudaStream_t);
+int pack_item_bias(const float*, const int32_t*, int64_t, float*, int64_t, float*, float*, cudaStream_t);
 int score_filter_f16(const void*, const float*, const float*, const float*, const void*, const float*, const float*,
-                     int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, float*, int32_t*, float*, int32_t*,
-                     cudaStream_t);
+                     const float*, const int32_t*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, float*, int32_t*,
+                     float*, int32_t*, cudaStream_t);
 int rescore_topk(const float*, const float*, const float*, const float*, const int32_t*, const float*, const int32_t*,
                  const float*, const float*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, int32_t, float*,
                  int32_t*, int32_t*, cudaStream_t);
@@ -149,24 +149,25 @@ int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32
   return trk::operand_stats(split, scale, rows, d_pad, out_norm, stats, trk::as_stream(stream));
 }
 
-int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
-                          void* out_hi, void* stream) {
-  return trk::rescale_hi_global(split, scale, stats, rows, d_pad, out_hi, trk::as_stream(stream));
+int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, const int32_t* perm,
+                          int64_t rows, int32_t d_pad, void* out_hi, void* stream) {
+  return trk::rescale_hi_global(split, scale, stats, perm, rows, d_pad, out_hi, trk::as_stream(stream));
 }
 
-int trk_pack_item_bias(const float* item_bias, int64_t n_items, float* out, int64_t n_items_padded, float* stats,
-                       void* stream) {
-  return trk::pack_item_bias(item_bias, n_items, out, n_items_padded, stats, trk::as_stream(stream));
+int trk_pack_item_bias(const float* item_bias, const int32_t* perm, int64_t n_items, float* out,
+                       int64_t n_items_padded, float* stats, float* block_max, void* stream) {
+  return trk::pack_item_bias(item_bias, perm, n_items, out, n_items_padded, stats, block_max, trk::as_stream(stream));
 }
 
 int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                          const float* user_norm, const void* item_hi_global, const float* item_stats,
-                         const float* item_bias_padded, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
-                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
-                         float* row_theta, int32_t* row_flags, void* stream) {
+                         const float* item_bias_padded, const float* block_bias_max, const int32_t* item_perm,
+                         int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
+                         int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
+                         int32_t* row_flags, void* stream) {
   return trk::score_filter_f16(user_split, user_scale, user_bias, user_norm, item_hi_global, item_stats,
-                               item_bias_padded, n_users, n_items, d_pad, k, n_splits, item_id_offset, cand_score,
-                               cand_item, row_theta, row_flags, trk::as_stream(stream));
+                               item_bias_padded, block_bias_max, item_perm, n_users, n_items, d_pad, k, n_splits,
+                               item_id_offset, cand_score, cand_item, row_theta, row_flags, trk::as_stream(stream));
 }
 
 int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,

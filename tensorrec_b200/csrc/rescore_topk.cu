@@ -118,32 +118,48 @@ rescore_topk_kernel(const float* __restrict__ user_repr, const float* __restrict
   }
 }
 
-// item biases padded to whole tiles with -inf (a padded column can never pass the filter) + max |bias| -> stats[2]
-__global__ void pack_item_bias_kernel(const float* __restrict__ bias, int64_t n, float* __restrict__ out,
-                                      int64_t n_padded, float* __restrict__ stats) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  float v = 0.0f;
-  if (i < n_padded) {
-    if (i < n) {
-      v = bias != nullptr ? bias[i] : 0.0f;
-      out[i] = v;
-    } else {
-      out[i] = -__int_as_float(0x7f800000);
-      v = 0.0f;
-    }
-  }
-  float a = fabsf(v);
+// item biases in processing order (out[p] = bias[perm[p]]), padded to whole tiles with -inf (a padded column can
+// never pass the filter); max |bias| -> stats[2]; block_max[b] = max bias of positions [128 b, 128 b + 128).
+__global__ void pack_item_bias_kernel(const float* __restrict__ bias, const int32_t* __restrict__ perm, int64_t n,
+                                      float* __restrict__ out, int64_t n_padded, float* __restrict__ stats,
+                                      float* __restrict__ block_max) {
+  // one warp per block of 128 positions
+  const int lane = threadIdx.x % 32;
+  const int64_t blk = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+  if (blk * 128 >= n_padded) return;
+  const float kNegInf = -__int_as_float(0x7f800000);
+  float vmax = kNegInf, amax = 0.0f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-  if (threadIdx.x % 32 == 0 && stats != nullptr && a > 0.0f) atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(a));
+  for (int q = 0; q < 4; ++q) {
+    const int64_t pos = blk * 128 + q * 32 + lane;
+    float v = kNegInf;
+    if (pos < n) {
+      const int64_t src = perm != nullptr ? perm[pos] : pos;
+      v = bias != nullptr ? bias[src] : 0.0f;
+      amax = fmaxf(amax, fabsf(v));
+    }
+    if (pos < n_padded) out[pos] = v;
+    vmax = fmaxf(vmax, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  if (lane == 0) {
+    if (block_max != nullptr) block_max[blk] = vmax;
+    if (stats != nullptr && amax > 0.0f) atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(amax));
+  }
 }
 
-int pack_item_bias(const float* bias, int64_t n, float* out, int64_t n_padded, float* stats, cudaStream_t stream) {
-  TRK_CHECK_ARG(out && n >= 0 && n_padded >= n, "pack_item_bias: bad arguments");
+int pack_item_bias(const float* bias, const int32_t* perm, int64_t n, float* out, int64_t n_padded, float* stats,
+                   float* block_max, cudaStream_t stream) {
+  TRK_CHECK_ARG(out && n >= 0 && n_padded >= n && n_padded % 128 == 0, "pack_item_bias: bad arguments");
   if (n_padded == 0) return TRK_OK;
   const int threads = 256;
-  pack_item_bias_kernel<<<static_cast<unsigned>(ceil_div(n_padded, threads)), threads, 0, stream>>>(bias, n, out,
-                                                                                                    n_padded, stats);
+  const int64_t n_blocks128 = n_padded / 128;
+  pack_item_bias_kernel<<<static_cast<unsigned>(ceil_div(n_blocks128, threads / 32)), threads, 0, stream>>>(
+      bias, perm, n, out, n_padded, stats, block_max);
   TRK_CHECK_LAUNCH();
   return TRK_OK;
 }

@@ -55,7 +55,9 @@ struct FilterParams {
   const float* user_scale;
   const float* user_bias;      // may be null
   const float* user_norm;      // |u|_2 per user
-  const float* item_bias;      // [n_tiles * 256], padding = -inf
+  const float* item_bias;      // [padded items] in PROCESSING order (see item_perm), padding = -inf
+  const float* block_bias_max; // max item bias of every block of 128 processing positions (-inf for all-padding)
+  const int32_t* item_perm;    // processing position -> local item index (items sorted by bias), or null = identity
   const float* item_stats;     // device: [0] = max_j |i_j|_2, [1] = global item scale (2^-E), [2] = max_j |bias_j|
   int64_t n_users;
   int64_t n_items;
@@ -174,47 +176,82 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   __syncwarp();
 }
 
-// 16 columns of one user row per lane: filter on v = acc + bias * inv_c.  The common case (no lane of the warp has a
-// column above its threshold) costs one vote and one uniform branch; otherwise the hitting lanes append their
-// survivors (with the approximate score) and rows whose buffer passed half full are compacted by the whole warp.
-__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t id_base, float c,
-                                          float inv_c, float ubias, float& tau, float& theta, float& drop_max,
-                                          float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
-  float v[16];
-  float vmax = -__int_as_float(0x7f800000);
+// 16 columns of one user row per lane.  The admission test is v_j = acc_j + bias_j / c > tau.  Items are processed in
+// bias-sorted order, so the biases of one 128-item block differ by ~1e-4 of their range and v_j <= max_j acc_j +
+// bmax_block / c is a tight upper bound: the fast path is a pure FMNMX3 reduction of the raw accumulators plus ONE add
+// (no per-score bias load, no per-score FFMA) and one vote; only when some lane's bound passes are the exact v_j
+// formed.  The hitting lanes then append their survivors (approximate score + original item id) and rows whose buffer
+// passed half full are compacted by the whole warp.
+// (Voting once per 32 columns instead measured 7-11 % SLOWER at 1M x 1M x d128; the 16-column granularity stays.)
+__device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
+  float amax = fmaxf(fmaxf(__uint_as_float(acc[0]), __uint_as_float(acc[1])),
+                     fmaxf(__uint_as_float(acc[2]), __uint_as_float(acc[3])));
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 b = f_lds128(bias_addr + q * 16);
-    v[4 * q + 0] = fmaf(b.x, inv_c, __uint_as_float(acc[4 * q + 0]));
-    v[4 * q + 1] = fmaf(b.y, inv_c, __uint_as_float(acc[4 * q + 1]));
-    v[4 * q + 2] = fmaf(b.z, inv_c, __uint_as_float(acc[4 * q + 2]));
-    v[4 * q + 3] = fmaf(b.w, inv_c, __uint_as_float(acc[4 * q + 3]));
-    vmax = fmaxf(vmax, fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3])));
-  }
-  const bool hit = vmax > tau;
-  if (__any_sync(0xffffffffu, hit)) {
-    if (hit) {
+  for (int q = 1; q < 4; ++q)
+    amax = fmaxf(amax, fmaxf(fmaxf(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])),
+                             fmaxf(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]))));
+  return amax;
+}
+
+// slow path of 16 columns: the lanes whose bound passed form the exact v_j and append their survivors, then rows
+// whose buffer passed half full are compacted by the whole warp.  Called warp-uniformly.
+__device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, uint32_t bias_addr, int32_t pos_base,
+                                         const int32_t* __restrict__ perm, int32_t id_offset, float c, float inv_c,
+                                         float ubias, float& tau, float& theta, float& drop_max, float m3,
+                                         uint32_t buf_row_addr, int& cnt, int lane, int k) {
+  if (hit) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (v[j] > tau) {
-          const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + f_lds32(bias_addr + j * 4);   // approximate score
-          if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
-            f_sts64(buf_row_addr + cnt * 8, a, id_base + j);
-            cnt += 1;
-          }
+    for (int j = 0; j < 16; ++j) {
+      const float b = f_lds32(bias_addr + j * 4);
+      const float v = fmaf(b, inv_c, __uint_as_float(acc[j]));
+      if (v > tau) {
+        const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + b;   // approximate score
+        if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
+          const int32_t pos = pos_base + j;
+          f_sts64(buf_row_addr + cnt * 8, a, id_offset + (perm != nullptr ? __ldg(perm + pos) : pos));
+          cnt += 1;
         }
       }
     }
-    __syncwarp();
-    unsigned need = __ballot_sync(0xffffffffu, cnt > kBufEntries - 16);
-    while (need) {
-      const int src = __ffs(need) - 1;
-      need &= need - 1;
-      compact_row(buf_row_addr, lane, src, k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
-    }
+  }
+  __syncwarp();
+  unsigned need = __ballot_sync(0xffffffffu, cnt > kBufEntries - 16);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    compact_row(buf_row_addr, lane, src, k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
   }
 }
 
+__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t pos_base,
+                                          const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
+                                          float c, float inv_c, float ubias, float& tau, float& theta,
+                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+  // inv_c is a power of two: bmax_scaled is exact and fl(amax + bmax_scaled) >= fl(acc_j + bias_j * inv_c) for all j
+  const bool hit = acc_max_16(acc) + bmax_scaled > tau;
+  if (__any_sync(0xffffffffu, hit))
+    admit_16(acc, hit, bias_addr, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
+             cnt, lane, k);
+}
+
+// 32 columns behind ONE vote (the two 16-column maxima are independent chains); the slow path still admits in
+// 16-column steps so that the 32-entry buffer cannot overflow between compactions.
+__device__ __forceinline__ void filter_32(const uint32_t* acc, uint32_t bias_addr, int32_t pos_base,
+                                          const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
+                                          float c, float inv_c, float ubias, float& tau, float& theta,
+                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+  const float a0 = acc_max_16(acc), a1 = acc_max_16(acc + 16);
+  if (__any_sync(0xffffffffu, fmaxf(a0, a1) + bmax_scaled > tau)) {
+    admit_16(acc, a0 + bmax_scaled > tau, bias_addr, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max,
+             m3, buf_row_addr, cnt, lane, k);
+    admit_16(acc + 16, a1 + bmax_scaled > tau, bias_addr + 64, pos_base + 16, perm, id_offset, c, inv_c, ubias, tau,
+             theta, drop_max, m3, buf_row_addr, cnt, lane, k);
+  }
+}
+
+__device__ long long g_filter_debug_clock[2];   // {SM cycles, ns} of CTA 0, written in the timing-experiment modes only
+
+template <int kVote>
 __global__ void __launch_bounds__(kFThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                     const FilterParams p) {
@@ -261,6 +298,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  long long dbg_clk = 0, dbg_ns = 0;
+  if (p.debug_mode != 0 && blockIdx.x == 0 && threadIdx.x == 64) {   // timing experiments: SM clock under this load
+    dbg_clk = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_ns));
+  }
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -293,6 +335,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
           __syncwarp();
           for (int kb = 0; kb < n_kb; ++kb) {
             const uint32_t s = fill % p.n_stages;
+            if (p.debug_mode == 6 && fill >= static_cast<uint32_t>(p.n_stages)) continue;   // timing: no B stream
             mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
             if (elect_one()) {
               mbar_arrive_expect_tx(b_full + s, kFBTileBytes);
@@ -329,7 +372,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
           uint32_t accumulate = 0;
           for (int kb = 0; kb < n_kb; ++kb) {
             const uint32_t s = fill % p.n_stages;
-            mbar_wait(b_full + s, (fill / p.n_stages) & 1);
+            if (!(p.debug_mode == 6 && fill >= static_cast<uint32_t>(p.n_stages)))
+              mbar_wait(b_full + s, (fill / p.n_stages) & 1);
             tcgen05_fence_after();
             const uint64_t db = umma_desc_k_major_sw128(b_base + s * kFBTileBytes);
             if (elect_one()) {
@@ -337,12 +381,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
               for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
                 const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
                 const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
-                if (p.debug_mode == 3 && t > t0 + 1) continue;   // timing experiment: epilogue without MMA work
+                if ((p.debug_mode == 3 || p.debug_mode == 5) && t > t0 + 1) continue;   // timing experiment: epilogue without MMA work
 #pragma unroll
                 for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
                   umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
               }
-              umma_commit(b_empty + s);
+              if (p.debug_mode != 6) umma_commit(b_empty + s);
             }
             __syncwarp();
             accumulate = 1;
@@ -382,7 +426,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       const float inv_c = 1.0f / c;
       // error bound of one approximate score: operand rounding + the fp32 rounding of the two bias adds
       const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
-      float tau = kNegInf, theta = kNegInf;
+      float tau = p.debug_mode == 4 ? -kNegInf : kNegInf, theta = kNegInf;   // 4: timing experiment, nothing admitted
       int cnt = 0;
       float drop_max = kNegInf;
 
@@ -393,16 +437,19 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (par * 2 + group) * kFBlockN;
         const uint32_t bias_base = smem_u32(smem + L.bias_off) + par * kFBiasBytes;
-        const int32_t id0 = p.item_id_offset + t * kFBlockN;
+        const int32_t pos0 = t * kFBlockN;
+        const float bmax_scaled = __ldg(p.block_bias_max + t) * inv_c;
         uint32_t ra[32], rb[32];
-        if (p.debug_mode == 2) goto drained;
-        if (p.debug_mode == 1) {
+        if (p.debug_mode == 2 || p.debug_mode == 6) goto drained;
+        if (p.debug_mode == 1 || p.debug_mode == 5) {   // 5: drain only, no MMA work either
           float acc_dbg = 0.0f;
-          for (int ch = 0; ch < kFBlockN / 32; ++ch) {
+          for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
             tmem_ld_32x32b_x32(taddr + ch * 32, ra);
+            tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc_dbg = fmaxf(acc_dbg, __uint_as_float(ra[j]));
+            for (int j = 0; j < 32; ++j)
+              acc_dbg = fmaxf(acc_dbg, fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
           }
           if (acc_dbg == 1.2345e30f) cnt = 1;
           goto drained;
@@ -412,16 +459,28 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 #pragma unroll 1
         for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
+          if (kVote == 32) {
+            filter_32(ra, bias_base + ch * 32 * 4, pos0 + ch * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c,
+                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
-                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+            for (int h = 0; h < 2; ++h)
+              filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, pos0 + ch * 32 + h * 16, p.item_perm,
+                        p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
+                        lane, p.k);
+          }
           tmem_ld_wait();
           if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
+          if (kVote == 32) {
+            filter_32(rb, bias_base + (ch + 1) * 32 * 4, pos0 + (ch + 1) * 32, p.item_perm, p.item_id_offset,
+                      bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
-                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+            for (int h = 0; h < 2; ++h)
+              filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, pos0 + (ch + 1) * 32 + h * 16,
+                        p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3,
+                        buf_row_addr, cnt, lane, p.k);
+          }
           tmem_ld_wait();
         }
       drained:
@@ -463,6 +522,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 
   tcgen05_fence_before();
   __syncthreads();
+  if (p.debug_mode != 0 && blockIdx.x == 0 && threadIdx.x == 64) {
+    long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_filter_debug_clock[0] = clock64() - dbg_clk;
+    g_filter_debug_clock[1] = ns - dbg_ns;
+  }
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<kFTmemCols>(tmem_base);
@@ -695,7 +760,8 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + par * kPTileN + group * 128;
         const uint32_t bias_base = smem_u32(smem + L.bias_off) + par * kPBiasBytes + group * 128 * 4;
-        const int32_t id0 = p.item_id_offset + t * kPTileN + group * 128;
+        const int32_t pos0 = t * kPTileN + group * 128;
+        const float bmax_scaled = __ldg(p.block_bias_max + 2 * t + group) * inv_c;
         uint32_t ra[32], rb[32];
         const float theta_before = theta;
         if (p.debug_mode == 2) goto drained2;
@@ -717,14 +783,16 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, id0 + ch * 32 + h * 16, c, inv_c, ubias, tau,
-                      theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, pos0 + ch * 32 + h * 16, p.item_perm,
+                      p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
+                      p.k);
           tmem_ld_wait();
           if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, id0 + (ch + 1) * 32 + h * 16, c, inv_c,
-                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, pos0 + (ch + 1) * 32 + h * 16, p.item_perm,
+                      p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
+                      p.k);
           tmem_ld_wait();
         }
         if (theta > theta_before) f_sts64(theta_mine, theta, epoch);   // publish the tightened threshold
@@ -808,16 +876,17 @@ __global__ void operand_stats_kernel(const __half* __restrict__ split, const flo
 // hi_global[r, :] = hi[r, :] * (scale_r / max_scale): an exact power-of-two rescale (values of small rows may fall
 // into the fp16 subnormal range -- that loss is inside the filter's error bound).
 __global__ void rescale_hi_global_kernel(const __half* __restrict__ split, const float* __restrict__ scale,
-                                         const float* __restrict__ stats, int64_t rows, int d_pad,
-                                         __half* __restrict__ out_hi) {
+                                         const float* __restrict__ stats, const int32_t* __restrict__ perm,
+                                         int64_t rows, int d_pad, __half* __restrict__ out_hi) {
   const float inv_max = 1.0f / fmaxf(stats[1], 1e-38f);
   const int64_t n_vec = rows * (d_pad / 8);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / (d_pad / 8);
+    const int64_t r = i / (d_pad / 8);                     // output row = processing position
     const int e = static_cast<int>(i % (d_pad / 8)) * 8;
-    const float f = scale[r] * inv_max;   // power of two <= 1
-    uint4 raw = *reinterpret_cast<const uint4*>(split + r * 2 * d_pad + e);
+    const int64_t src = perm != nullptr ? perm[r] : r;     // the item placed at that position
+    const float f = scale[src] * inv_max;   // power of two <= 1
+    uint4 raw = *reinterpret_cast<const uint4*>(split + src * 2 * d_pad + e);
     __half2* h = reinterpret_cast<__half2*>(&raw);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -891,8 +960,8 @@ int operand_stats(const void* split, const float* scale, int64_t rows, int32_t d
   return TRK_OK;
 }
 
-int rescale_hi_global(const void* split, const float* scale, const float* stats, int64_t rows, int32_t d_pad,
-                      void* out_hi, cudaStream_t stream) {
+int rescale_hi_global(const void* split, const float* scale, const float* stats, const int32_t* perm, int64_t rows,
+                      int32_t d_pad, void* out_hi, cudaStream_t stream) {
   TRK_CHECK_ARG(split && scale && stats && out_hi && rows >= 0 && d_pad >= 64 && d_pad % 64 == 0,
                 "rescale_hi_global: bad arguments");
   if (rows == 0) return TRK_OK;
@@ -900,17 +969,19 @@ int rescale_hi_global(const void* split, const float* scale, const float* stats,
   const int64_t blocks = ceil_div(rows * (d_pad / 8), threads);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   rescale_hi_global_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
-      static_cast<const __half*>(split), scale, stats, rows, d_pad, static_cast<__half*>(out_hi));
+      static_cast<const __half*>(split), scale, stats, perm, rows, d_pad, static_cast<__half*>(out_hi));
   TRK_CHECK_LAUNCH();
   return TRK_OK;
 }
 
 int score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                      const float* user_norm, const void* item_hi, const float* item_stats, const float* item_bias,
-                     int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
+                     const float* block_bias_max, const int32_t* item_perm, int64_t n_users, int64_t n_items,
+                     int32_t d_pad, int32_t k, int32_t n_splits,
                      int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
                      int32_t* row_flags, cudaStream_t stream) {
-  TRK_CHECK_ARG(user_split && user_scale && user_norm && item_hi && item_stats && item_bias, "score_filter: null input");
+  TRK_CHECK_ARG(user_split && user_scale && user_norm && item_hi && item_stats && item_bias && block_bias_max,
+                "score_filter: null input");
   TRK_CHECK_ARG(cand_score && cand_item && row_theta && row_flags, "score_filter: null output");
   TRK_CHECK_ARG(n_users >= 1 && n_items >= 1 && n_splits >= 1, "score_filter: empty shape");
   TRK_CHECK_ARG(n_users < (1ll << 31) && n_items < (1ll << 31) - 512, "score_filter: shape exceeds int32 indexing");
@@ -931,6 +1002,8 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.user_bias = user_bias;
   p.user_norm = user_norm;
   p.item_bias = item_bias;
+  p.block_bias_max = block_bias_max;
+  p.item_perm = item_perm;
   p.item_stats = item_stats;
   p.n_users = n_users;
   p.n_items = n_items;
@@ -1004,11 +1077,20 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   if (rc != TRK_OK) return rc;
 
   const uint32_t smem_bytes = filter_layout(p.n_kblocks, p.n_stages).total + 1024;
-  TRK_CHECK_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const char* vote = getenv("TRK_FILTER_VOTE");
+  auto kernel = (vote != nullptr && atoi(vote) == 16) ? score_filter_kernel<16> : score_filter_kernel<32>;
+  TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
   const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
-  score_filter_kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_users, map_items, p);
+  kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_users, map_items, p);
   TRK_CHECK_LAUNCH();
+  if (p.debug_mode != 0) {   // timing experiments only: report the SM clock CTA 0 saw (synchronises)
+    long long clk[2] = {0, 0};
+    TRK_CHECK_CUDA(cudaStreamSynchronize(stream));
+    TRK_CHECK_CUDA(cudaMemcpyFromSymbol(clk, g_filter_debug_clock, sizeof(clk)));
+    fprintf(stderr, "[trk] score_filter debug=%d: %lld cycles in %.3f ms -> %.0f MHz\n", p.debug_mode, clk[0],
+            clk[1] * 1e-6, clk[1] > 0 ? clk[0] * 1e3 / static_cast<double>(clk[1]) : 0.0);
+  }
   return TRK_OK;
 }
 

@@ -271,26 +271,36 @@ def operand_stats(split, scale, d_pad, want_norm=True, stats=None):
     return norm
 
 
-def rescale_hi_global(split, scale, stats, d_pad):
+def rescale_hi_global(split, scale, stats, d_pad, perm=None):
     lib = require_cuda()
     rows = split.shape[0]
     out = torch.empty((rows, int(d_pad)), dtype=torch.float16, device=split.device)
-    rc = lib.trk_rescale_hi_global(_p(split), _p(scale), _p(stats), rows, int(d_pad), _p(out), _stream())
+    rc = lib.trk_rescale_hi_global(_p(split), _p(scale), _p(stats), _p(perm), rows, int(d_pad), _p(out), _stream())
     _lib.check(rc, 'trk_rescale_hi_global')
     return out
 
 
-def pack_item_bias(item_bias, n_items, stats, device):
+def pack_item_bias(item_bias, n_items, stats, device, perm=None):
+    """Returns (bias in processing order padded with -inf, max bias per block of 128 positions)."""
     lib = require_cuda()
     n_pad = padded_items(n_items)
     out = torch.empty((n_pad,), dtype=torch.float32, device=device)
-    rc = lib.trk_pack_item_bias(_p(item_bias), n_items, _p(out), n_pad, _p(stats), _stream())
+    block_max = torch.empty((n_pad // 128,), dtype=torch.float32, device=device)
+    rc = lib.trk_pack_item_bias(_p(item_bias), _p(perm), n_items, _p(out), n_pad, _p(stats), _p(block_max), _stream())
     _lib.check(rc, 'trk_pack_item_bias')
-    return out
+    return out, block_max
 
 
-def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_stats, item_bias_pad, n_users, n_items,
-                 d_pad, k, n_splits=None, item_id_offset=0):
+def bias_processing_order(item_bias):
+    """Items by DESCENDING bias (stable, so the order is deterministic): int32 perm[position] = item index.
+    Highest biases first: the running k-th best rises early, and every later block starts below it by its bias gap."""
+    if item_bias is None:
+        return None
+    return torch.sort(item_bias, descending=True, stable=True).indices.to(torch.int32)
+
+
+def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_stats, item_bias_pad, block_bias_max,
+                 item_perm, n_users, n_items, d_pad, k, n_splits=None, item_id_offset=0):
     lib = require_cuda()
     if n_splits is None:
         n_splits = default_splits(n_users, n_items)
@@ -301,7 +311,8 @@ def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_sta
     theta = torch.empty((n_users, n_splits, 2), dtype=torch.float32, device=dev)
     flags = torch.empty((n_users, n_splits, 2), dtype=torch.int32, device=dev)
     rc = lib.trk_score_filter_f16(_p(user_split), _p(user_scale), _p(user_bias), _p(user_norm), _p(item_hi),
-                                  _p(item_stats), _p(item_bias_pad), n_users, n_items, int(d_pad), int(k),
+                                  _p(item_stats), _p(item_bias_pad), _p(block_bias_max), _p(item_perm), n_users,
+                                  n_items, int(d_pad), int(k),
                                   int(n_splits), int(item_id_offset), _p(cand_s), _p(cand_i), _p(theta), _p(flags),
                                   _stream())
     _lib.check(rc, 'trk_score_filter_f16')
@@ -341,23 +352,30 @@ def topk_exact(users, items, k, n_splits=None, item_id_offset=0):
     return topk_merge(cs, ci, k)
 
 
-def topk_filter(users, items, k, n_splits=None, item_id_offset=0, info=None):
-    """Filter form: one tensor pass + exact fp32 re-scoring; users whose error bound cannot be certified (buffer
-    overflow under massive ties, bound violated) are re-run through the exact kernel.  Needs users/items.repr_f32."""
-    dev = users.split.device
-    stats = torch.zeros((3,), dtype=torch.float32, device=dev)
-    user_norm = operand_stats(users.split, users.scale, users.d_pad)
-    operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=stats)
-    item_hi = rescale_hi_global(items.split, items.scale, stats, items.d_pad)
-    bias_pad = pack_item_bias(items.bias, items.n_rows, stats, dev)
-    cs, ci, theta, flags = score_filter(users.split, users.scale, users.bias, user_norm, item_hi, stats, bias_pad,
-                                        users.n_rows, items.n_rows, users.d_pad, k, n_splits=n_splits,
-                                        item_id_offset=item_id_offset)
-    top_s, top_i, bad = rescore_topk(users.repr_f32, items.repr_f32, users.bias, items.bias, ci, theta, flags,
-                                     user_norm, stats, k, item_id_offset=item_id_offset)
-    n_bad = int(bad.sum().item())          # the only host sync of the path
-    if info is not None:
-        info['fallback_rows'] = n_bad
+class FilterItems(object):
+    """Item-side inputs of the filter kernel, derived once per call from the K1 outputs."""
+
+    def __init__(self, items):
+        dev = items.split.device
+        self.stats = torch.zeros((3,), dtype=torch.float32, device=dev)
+        operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=self.stats)
+        self.perm = bias_processing_order(items.bias)
+        self.hi = rescale_hi_global(items.split, items.scale, self.stats, items.d_pad, perm=self.perm)
+        self.bias_pad, self.block_max = pack_item_bias(items.bias, items.n_rows, self.stats, dev, perm=self.perm)
+
+
+def filter_and_rescore(users, items, fitems, user_norm, k, n_splits=None, item_id_offset=0):
+    """(top scores [U,k], top ids [U,k], flags [U]) -- flags mark users the certificate did not cover."""
+    cs, ci, theta, flags = score_filter(users.split, users.scale, users.bias, user_norm, fitems.hi, fitems.stats,
+                                        fitems.bias_pad, fitems.block_max, fitems.perm, users.n_rows, items.n_rows,
+                                        users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset)
+    return rescore_topk(users.repr_f32, items.repr_f32, users.bias, items.bias, ci, theta, flags, user_norm,
+                        fitems.stats, k, item_id_offset=item_id_offset)
+
+
+def rerun_uncertified(users, items, bad, top_s, top_i, k, item_id_offset=0):
+    """Users flagged by the certificate go through the exact kernel; returns how many there were (one host sync)."""
+    n_bad = int(bad.sum().item())
     if n_bad:
         idx = bad.nonzero(as_tuple=True)[0]
         sub = SideOperands(None, users.split.index_select(0, idx).contiguous(), users.scale.index_select(0, idx),
@@ -366,4 +384,17 @@ def topk_filter(users, items, k, n_splits=None, item_id_offset=0, info=None):
         ex_s, ex_i = topk_exact(sub, items, k, item_id_offset=item_id_offset)
         top_s.index_copy_(0, idx, ex_s)
         top_i.index_copy_(0, idx, ex_i)
+    return n_bad
+
+
+def topk_filter(users, items, k, n_splits=None, item_id_offset=0, info=None):
+    """Filter form: one tensor pass + exact fp32 re-scoring; users whose error bound cannot be certified (buffer
+    overflow under massive ties, bound violated) are re-run through the exact kernel.  Needs users/items.repr_f32."""
+    user_norm = operand_stats(users.split, users.scale, users.d_pad)
+    fitems = FilterItems(items)
+    top_s, top_i, bad = filter_and_rescore(users, items, fitems, user_norm, k, n_splits=n_splits,
+                                           item_id_offset=item_id_offset)
+    n_bad = rerun_uncertified(users, items, bad, top_s, top_i, k, item_id_offset=item_id_offset)
+    if info is not None:
+        info['fallback_rows'] = n_bad
     return top_s, top_i

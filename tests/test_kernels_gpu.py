@@ -368,10 +368,22 @@ def test_operand_stats_and_global_rescale(K):
     x = items.repr_f32.cpu().numpy()
     rec = hi[:, :100] * st[1]
     assert np.all(np.abs(rec - x) <= 2.0 ** -11 * np.abs(x) + 2.0 ** -24 * np.abs(x).max())
-    padded = K.pack_item_bias(items.bias, 1000, stats, 'cuda').cpu().numpy()
+    padded, bmax = K.pack_item_bias(items.bias, 1000, stats, 'cuda')
+    padded, bmax = padded.cpu().numpy(), bmax.cpu().numpy()
+    bias = items.bias.cpu().numpy()
     assert padded.shape == (1024,) and np.all(np.isneginf(padded[1000:]))
-    assert np.array_equal(padded[:1000], items.bias.cpu().numpy())
-    assert stats.cpu().numpy()[2] == np.abs(items.bias.cpu().numpy()).max()
+    assert np.array_equal(padded[:1000], bias)
+    assert np.array_equal(bmax, padded.reshape(-1, 128).max(axis=1))
+    assert stats.cpu().numpy()[2] == np.abs(bias).max()
+    # processing order: items sorted by bias (stable), operands and biases permuted alike
+    perm = K.bias_processing_order(items.bias)
+    pn = perm.cpu().numpy()
+    assert np.array_equal(pn, np.argsort(-bias, kind='stable'))
+    hi_p = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad, perm=perm).float().cpu().numpy()
+    assert np.array_equal(hi_p, hi[pn])
+    padded_p, bmax_p = K.pack_item_bias(items.bias, 1000, stats, 'cuda', perm=perm)
+    assert np.array_equal(padded_p.cpu().numpy()[:1000], bias[pn])
+    assert np.array_equal(bmax_p.cpu().numpy(), padded_p.cpu().numpy().reshape(-1, 128).max(axis=1))
 
 
 @pytest.mark.parametrize('U,I,d,k,regime,cosine,splits', [
@@ -411,7 +423,8 @@ def test_filter_topk_integer_fixture_exact_through_fallback(K, U, I, d, k, split
     assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
 
 
-def test_filter_candidates_respect_the_error_bound(K):
+@pytest.mark.parametrize('sort_by_bias', [True, False])
+def test_filter_candidates_respect_the_error_bound(K, sort_by_bias):
     """The approximate scores of the survivors are within m = 1.5*2^-10 |u| max|i| of the exact ones, and every true
     top-k item is among the survivors."""
     import torch
@@ -421,10 +434,11 @@ def test_filter_candidates_respect_the_error_bound(K):
     stats = torch.zeros(3, device='cuda')
     unorm = K.operand_stats(users.split, users.scale, users.d_pad)
     K.operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=stats)
-    hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad)
-    bias_pad = K.pack_item_bias(items.bias, I, stats, 'cuda')
-    cs, ci, theta, flags = K.score_filter(users.split, users.scale, users.bias, unorm, hi, stats, bias_pad, U, I,
-                                          users.d_pad, k, n_splits=2)
+    perm = K.bias_processing_order(items.bias) if sort_by_bias else None
+    hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad, perm=perm)
+    bias_pad, bmax = K.pack_item_bias(items.bias, I, stats, 'cuda', perm=perm)
+    cs, ci, theta, flags = K.score_filter(users.split, users.scale, users.bias, unorm, hi, stats, bias_pad, bmax, perm,
+                                          U, I, users.d_pad, k, n_splits=2)
     scores = oracle_scores(uf, itf, wu, wi, bu, bi)
     cs, ci = cs.cpu().numpy().reshape(U, -1), ci.cpu().numpy().reshape(U, -1)
     m = 1.5 * 2.0 ** -10 * unorm.cpu().numpy() * stats.cpu().numpy()[0] + 1e-5
