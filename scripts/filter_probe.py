@@ -49,16 +49,7 @@ pairs = A.users * float(A.items)
 os.environ['TRK_FILTER_FORM'] = 'single'
 ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
 print('filter single-CTA form: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
-for vote in ('16', '32'):
-    os.environ['TRK_FILTER_VOTE'] = vote
-    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
-    print('single form, vote per %s columns: %.2f ms' % (vote, ms))
-    os.environ['TRK_FILTER_DEBUG'] = '4'
-    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
-    print('single form, vote per %s columns, nothing admitted: %.2f ms' % (vote, ms))
-    os.environ['TRK_FILTER_DEBUG'] = '0'
-os.environ.pop('TRK_FILTER_VOTE')
-for mode in ('7', '1', '2', '6'):
+for mode in ('7', '4', '1', '2', '6'):
     os.environ['TRK_FILTER_DEBUG'] = mode
     ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
     print('single form debug=%s: %.2f ms' % (mode, ms))

@@ -35,14 +35,15 @@
 namespace trk {
 
 constexpr int kFBlockM = 128;
-constexpr int kFBlockN = 128;          // item tile: 4 accumulators of 128 columns fill the 512 TMEM columns
+constexpr int kFBlockN = 128;          // item tile; TMEM: 128 columns of A operand + 3 accumulators of 128 columns
+constexpr int kFAccSlots = 3;
+constexpr uint32_t kFTmemAccCol = 128;   // first accumulator column (columns [0, 128): user operand, 64 per block)
 constexpr int kFKBlock = 64;
 constexpr int kFUmmaK = 16;
 constexpr int kFThreads = 384;
 constexpr uint32_t kFATileBytes = kFBlockM * kFKBlock * 2;   // 16 KB
 constexpr uint32_t kFBTileBytes = kFBlockN * kFKBlock * 2;   // 16 KB
-constexpr uint32_t kFBiasBytes = kFBlockN * 4;               // 512 B
-constexpr int kFMaxStages = 8;
+constexpr int kFMaxStages = 10;
 constexpr uint32_t kFTmemCols = 512;
 constexpr int kBufEntries = 32;      // candidate buffer per (row, epilogue group)
 constexpr int kKeepMax = 16;         // entries kept by a compaction (>= k + slack); also the per-group output width
@@ -52,6 +53,7 @@ constexpr float kBiasUlps = 4.0f * 1.1920929e-7f;        // 4 ulp(1): rounding o
 constexpr float kThetaMargins = 2.25f;                   // theta = a_k - 2.25 m  (> 2 m is what the proof needs)
 
 struct FilterParams {
+  const __half* user_split;    // [n_users, 2 d_pad] hi | lo; the filter reads the hi half
   const float* user_scale;
   const float* user_bias;      // may be null
   const float* user_norm;      // |u|_2 per user
@@ -62,6 +64,7 @@ struct FilterParams {
   int64_t n_users;
   int64_t n_items;
   int32_t n_kblocks;           // d_pad / 64
+  int32_t d_pad;
   int32_t n_stages;
   int32_t k;
   int32_t n_splits;
@@ -70,7 +73,7 @@ struct FilterParams {
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
-                               // 3 = full epilogue but no MMA issued after the first two tiles (stale accumulators)
+                               // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
   float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
   float* row_theta;            // [n_users, n_splits, 2] final admission threshold
@@ -78,24 +81,26 @@ struct FilterParams {
 };
 
 struct FilterLayout {
-  uint32_t a_off, b_off, buf_off, bias_off, bar_off, total;
+  uint32_t b_off, buf_off, bar_off, total;
 };
-__host__ __device__ inline FilterLayout filter_layout(int n_kblocks, int n_stages) {
+__host__ __device__ inline FilterLayout filter_layout(int n_stages) {
   FilterLayout L;
-  L.a_off = 0;
-  L.b_off = L.a_off + 2u * static_cast<uint32_t>(n_kblocks) * kFATileBytes;   // two user blocks
+  L.b_off = 0;
   L.buf_off = L.b_off + static_cast<uint32_t>(n_stages) * kFBTileBytes;
-  L.bias_off = L.buf_off + 2u * kFBlockM * kBufEntries * 8u;      // 64 KB of candidate buffers
-  L.bar_off = L.bias_off + 2u * kFBiasBytes;                      // one slot per tile parity
+  L.bar_off = L.buf_off + 2u * kFBlockM * kBufEntries * 8u;       // 64 KB of candidate buffers
   L.total = L.bar_off + 512u;
   return L;
 }
-// barriers (uint64): [0] a_full [1] a_empty [2..3] tmem_full [4..5] tmem_empty [6..7] bias_full [8..9] bias_empty
-// [10 .. 10+S) b_full [10+S .. 10+2S) b_empty ; TMEM base address (uint32) at byte 400 of the block.
-// Tile `it` has parity par = it & 1: its two accumulators (user block 0 / 1) are TMEM slots par*2 + {0,1}, its biases
-// sit in bias slot par; both epilogue groups wait on tmem_full[par] / bias_full[par] and release tmem_empty[par] /
-// bias_empty[par] (8 warp arrivals).  Parity double-buffers the accumulators: the MMA warp fills one pair while the
-// groups drain the other (with a single accumulator per group the two phases serialise: profiles/r1_v3_filter_ncu.json).
+// The B ring is organised in TILE slots of n_kblocks k-blocks (16 KB each): one full / one empty barrier per item tile.
+// barriers (uint64): [0..1] a_full (per user block) [2..4] tmem_full [5..7] tmem_empty [8 .. 8+T) b_full
+// [8+T .. 8+2T) b_empty, T = n_stages / n_kblocks tile slots; TMEM base address (uint32) at byte 400 of the block.
+// Accumulators: (tile it, user block b) is number q = 2 it + b and lives in TMEM slot q % 3 (its n-th use, n = q / 3,
+// has barrier parity n & 1).  Epilogue group b drains the accumulators of user block b: while it works on one, the
+// MMA warp can fill the next of either block.
+// The item biases are NOT staged: the hot loop needs only the block maximum (one cached global load per tile,
+// prefetched a tile ahead) and the rare admission path reads the few biases it needs through L2.  (A two-slot
+// shared-memory ring fed by one bulk copy per tile put the copy's ~2 us latency on the critical path of every
+// second tile: TRK_FILTER_DEBUG=6 showed 112 cycles per MMA step against 64 for the bare instruction stream.)
 
 __device__ __forceinline__ float4 f_lds128(uint32_t addr) {
   float4 v;
@@ -195,14 +200,14 @@ __device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
 
 // slow path of 16 columns: the lanes whose bound passed form the exact v_j and append their survivors, then rows
 // whose buffer passed half full are compacted by the whole warp.  Called warp-uniformly.
-__device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, uint32_t bias_addr, int32_t pos_base,
+__device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, const float* __restrict__ bias, int32_t pos_base,
                                          const int32_t* __restrict__ perm, int32_t id_offset, float c, float inv_c,
                                          float ubias, float& tau, float& theta, float& drop_max, float m3,
                                          uint32_t buf_row_addr, int& cnt, int lane, int k) {
   if (hit) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float b = f_lds32(bias_addr + j * 4);
+      const float b = __ldg(bias + pos_base + j);   // rare path: the padded, processing-order bias array (L2 resident)
       const float v = fmaf(b, inv_c, __uint_as_float(acc[j]));
       if (v > tau) {
         const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + b;   // approximate score
@@ -223,71 +228,63 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, uint32_t
   }
 }
 
-__device__ __forceinline__ void filter_16(const uint32_t* acc, uint32_t bias_addr, int32_t pos_base,
+__device__ __forceinline__ void filter_16(const uint32_t* acc, const float* __restrict__ bias, int32_t pos_base,
                                           const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
                                           float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
   // inv_c is a power of two: bmax_scaled is exact and fl(amax + bmax_scaled) >= fl(acc_j + bias_j * inv_c) for all j
   const bool hit = acc_max_16(acc) + bmax_scaled > tau;
   if (__any_sync(0xffffffffu, hit))
-    admit_16(acc, hit, bias_addr, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
-             cnt, lane, k);
+    admit_16(acc, hit, bias, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
+             lane, k);
 }
 
 // 32 columns behind ONE vote (the two 16-column maxima are independent chains); the slow path still admits in
 // 16-column steps so that the 32-entry buffer cannot overflow between compactions.
-__device__ __forceinline__ void filter_32(const uint32_t* acc, uint32_t bias_addr, int32_t pos_base,
+__device__ __forceinline__ void filter_32(const uint32_t* acc, const float* __restrict__ bias, int32_t pos_base,
                                           const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
                                           float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
   const float a0 = acc_max_16(acc), a1 = acc_max_16(acc + 16);
   if (__any_sync(0xffffffffu, fmaxf(a0, a1) + bmax_scaled > tau)) {
-    admit_16(acc, a0 + bmax_scaled > tau, bias_addr, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max,
-             m3, buf_row_addr, cnt, lane, k);
-    admit_16(acc + 16, a1 + bmax_scaled > tau, bias_addr + 64, pos_base + 16, perm, id_offset, c, inv_c, ubias, tau,
-             theta, drop_max, m3, buf_row_addr, cnt, lane, k);
+    admit_16(acc, a0 + bmax_scaled > tau, bias, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3,
+             buf_row_addr, cnt, lane, k);
+    admit_16(acc + 16, a1 + bmax_scaled > tau, bias, pos_base + 16, perm, id_offset, c, inv_c, ubias, tau, theta,
+             drop_max, m3, buf_row_addr, cnt, lane, k);
   }
 }
 
 __device__ long long g_filter_debug_clock[2];   // {SM cycles, ns} of CTA 0, written in the timing-experiment modes only
 
-template <int kVote>
+template <int kNKB>   // k-blocks of 64 per row: d_pad / 64
 __global__ void __launch_bounds__(kFThreads, 1)
-score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
-                    const FilterParams p) {
+score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const FilterLayout L = filter_layout(p.n_kblocks, p.n_stages);
+  const FilterLayout L = filter_layout(p.n_stages);
+  const int n_slots = p.n_stages / kNKB;   // B tile slots
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* a_full = bars + 0;
-  uint64_t* a_empty = bars + 1;
-  uint64_t* tmem_full = bars + 2;     // [tile parity]
-  uint64_t* tmem_empty = bars + 4;
-  uint64_t* bias_full = bars + 6;
-  uint64_t* bias_empty = bars + 8;
-  uint64_t* b_full = bars + 10;
-  uint64_t* b_empty = bars + 10 + p.n_stages;
+  uint64_t* a_full = bars + 0;        // [user block]
+  uint64_t* tmem_full = bars + 2;     // [accumulator slot]
+  uint64_t* tmem_empty = bars + 5;
+  uint64_t* b_full = bars + 8;
+  uint64_t* b_empty = bars + 8 + n_slots;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
+  constexpr uint32_t kSlotBytes = kNKB * kFBTileBytes;
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
-  const int n_kb = p.n_kblocks;
+  constexpr int n_kb = kNKB;
   const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * p.n_splits;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_users);
-    tma_prefetch_desc(&map_items);
-  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_items);
   if (warp == 1 && lane == 0) {
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i) mbar_init(a_full + i, 4);
+    for (int i = 0; i < kFAccSlots; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 8);
-      mbar_init(bias_full + i, 1);
-      mbar_init(bias_empty + i, 8);
+      mbar_init(tmem_empty + i, 4);
     }
-    for (int i = 0; i < p.n_stages; ++i) {
+    for (int i = 0; i < n_slots; ++i) {
       mbar_init(b_full + i, 1);
       mbar_init(b_empty + i, 1);
     }
@@ -307,43 +304,27 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     {   // warp-uniform control flow, one elected lane issues (see the MMA warp)
-      uint32_t fill = 0, witer = 0, it = 0;
+      int ts = 0;
+      uint32_t ts_phase = 0, filled = 0;
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int up = static_cast<int>(w % p.n_user_pairs);
         const int sp = static_cast<int>(w / p.n_user_pairs);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        if (t1 <= t0) continue;
-        mbar_wait(a_empty, (witer & 1) ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(a_full, 2 * n_kb * kFATileBytes);
-          for (int b = 0; b < 2; ++b)
-            for (int kb = 0; kb < n_kb; ++kb)   // the hi half of the user operand: k-blocks [0, n_kb); rows past
-              tma_load_2d(smem + L.a_off + (b * n_kb + kb) * kFATileBytes, &map_users, a_full, kb * kFKBlock,
-                          (up * 2 + b) * kFBlockM, kEvictFirst);   // n_users are zero-filled by TMA
-        }
-        __syncwarp();
-        ++witer;
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t par = it & 1, use = it >> 1;
-          mbar_wait(bias_empty + par, (use & 1) ^ 1);
+        for (int t = t0; t < t1; ++t) {
+          if (p.debug_mode == 6 && filled >= static_cast<uint32_t>(n_slots)) continue;   // timing: no B stream
+          mbar_wait(b_empty + ts, ts_phase ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(bias_full + par, kFBiasBytes);
-            bulk_load_1d(smem + L.bias_off + par * kFBiasBytes, p.item_bias + static_cast<int64_t>(t) * kFBlockN,
-                         kFBiasBytes, bias_full + par);
+            mbar_arrive_expect_tx(b_full + ts, kSlotBytes);
+#pragma unroll
+            for (int kb = 0; kb < kNKB; ++kb)
+              tma_load_2d(smem + L.b_off + ts * kSlotBytes + kb * kFBTileBytes, &map_items, b_full + ts, kb * kFKBlock,
+                          t * kFBlockN, kEvictLast);
           }
           __syncwarp();
-          for (int kb = 0; kb < n_kb; ++kb) {
-            const uint32_t s = fill % p.n_stages;
-            if (p.debug_mode == 6 && fill >= static_cast<uint32_t>(p.n_stages)) continue;   // timing: no B stream
-            mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(b_full + s, kFBTileBytes);
-              tma_load_2d(smem + L.b_off + s * kFBTileBytes, &map_items, b_full + s, kb * kFKBlock, t * kFBlockN,
-                          kEvictLast);
-            }
-            __syncwarp();
-            ++fill;
+          ++filled;
+          if (++ts == n_slots) {
+            ts = 0;
+            ts_phase ^= 1;
           }
         }
       }
@@ -353,50 +334,63 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     // The whole warp runs the (warp-uniform) control flow and polls the barriers; one elected lane issues.  Issuing
     // from inside `if (lane == 0)` makes ptxas wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (~17
     // instructions per MMA) because it cannot prove the operands uniform.
+    //
+    // The user operand is read from TENSOR MEMORY (tcgen05.mma [d], [a], b-desc): with both operands in shared memory
+    // an M = 128, N = 128, K = 16 step takes 77 cycles instead of the 64 of the math (scripts/mma_probe).
+    //
+    // This loop has to stay LEAN: one thread issues every MMA of the SM, and 8 MMA steps are only 512 cycles of tensor
+    // work.  With a runtime stage count the ring arithmetic (fill % n_stages, fill / n_stages: ~25 dependent
+    // instructions each through I2F / MUFU.RCP / F2I) plus the R2UR moves put ~450 cycles of scalar latency in front of
+    // every 4 steps and the pipe ran at 112 cycles per step (TRK_FILTER_DEBUG=6).  Now: ring positions advance
+    // incrementally, one full/empty barrier per item tile, all 8 steps of an accumulator issued from one elected
+    // block with compile-time offsets.
     {
       constexpr uint32_t idesc = umma_idesc_f16_f32(kFBlockM, kFBlockN);
-      uint32_t fill = 0, witer = 0, it = 0;
-      const uint32_t a_base = smem_u32(smem + L.a_off);
+      int ts = 0;
+      uint32_t ts_phase = 0, witer = 0, slot = 0, slot_phase = 0, consumed = 0;
       const uint32_t b_base = smem_u32(smem + L.b_off);
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int sp = static_cast<int>(w / p.n_user_pairs);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
-        mbar_wait(a_full, witer & 1);
+        mbar_wait(a_full + 0, witer & 1);   // both groups have written their user block into tensor memory
+        mbar_wait(a_full + 1, witer & 1);
+        tcgen05_fence_after();
         ++witer;
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t par = it & 1, use = it >> 1;
-          mbar_wait(tmem_empty + par, (use & 1) ^ 1);   // both groups have drained this accumulator pair
-          tcgen05_fence_after();
-          uint32_t accumulate = 0;
-          for (int kb = 0; kb < n_kb; ++kb) {
-            const uint32_t s = fill % p.n_stages;
-            if (!(p.debug_mode == 6 && fill >= static_cast<uint32_t>(p.n_stages)))
-              mbar_wait(b_full + s, (fill / p.n_stages) & 1);
+        for (int t = t0; t < t1; ++t) {
+          const bool streamed = !(p.debug_mode == 6 && consumed >= static_cast<uint32_t>(n_slots));
+          if (streamed) mbar_wait(b_full + ts, ts_phase);
+          const uint64_t db = umma_desc_k_major_sw128(b_base + ts * kSlotBytes);
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {     // one B tile, two user blocks, one accumulator each
+            mbar_wait(tmem_empty + slot, slot_phase ^ 1);
             tcgen05_fence_after();
-            const uint64_t db = umma_desc_k_major_sw128(b_base + s * kFBTileBytes);
+            const uint32_t d_tmem = tmem_base + kFTmemAccCol + slot * kFBlockN;
+            const uint32_t a_tmem = tmem_base + b * 64;
             if (elect_one()) {
 #pragma unroll
-              for (int b = 0; b < 2; ++b) {   // one B tile, two user blocks
-                const uint64_t da = umma_desc_k_major_sw128(a_base + (b * n_kb + kb) * kFATileBytes);
-                const uint32_t d_tmem = tmem_base + (par * 2 + b) * kFBlockN;
-                if ((p.debug_mode == 3 || p.debug_mode == 5) && t > t0 + 1) continue;   // timing experiment: epilogue without MMA work
+              for (int kb = 0; kb < kNKB; ++kb)
 #pragma unroll
                 for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
-                  umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
-              }
-              if (p.debug_mode != 6) umma_commit(b_empty + s);
+                  umma_f16_ts(d_tmem, a_tmem + kb * (kFKBlock / 2) + ks * (kFUmmaK / 2),
+                              db + static_cast<uint64_t>(kb * (kFBTileBytes >> 4) + 2 * ks), idesc,
+                              static_cast<uint32_t>(kb > 0 || ks > 0));
+              umma_commit(tmem_full + slot);
+              if (b == 1 && streamed) umma_commit(b_empty + ts);
             }
             __syncwarp();
-            accumulate = 1;
-            ++fill;
+            if (++slot == kFAccSlots) {
+              slot = 0;
+              slot_phase ^= 1;
+            }
           }
-          if (elect_one()) umma_commit(tmem_full + par);
-          __syncwarp();
+          ++consumed;
+          if (++ts == n_slots) {
+            ts = 0;
+            ts_phase ^= 1;
+          }
         }
-        if (elect_one()) umma_commit(a_empty);
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -410,7 +404,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
     const float max_item_norm = __ldg(p.item_stats + 0);
     const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
     const float max_item_bias = __ldg(p.item_stats + 2);
-    uint32_t it = 0;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t slot = group, slot_use = 0;   // accumulator number q = 2 (tile count) + group: slot q % 3, use q / 3
 
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int up = static_cast<int>(w % p.n_user_pairs);
@@ -429,19 +424,40 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
       float tau = p.debug_mode == 4 ? -kNegInf : kNegInf, theta = kNegInf;   // 4: timing experiment, nothing admitted
       int cnt = 0;
       float drop_max = kNegInf;
+      uint32_t ra[32], rb[32];
 
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t par = it & 1, use = it >> 1;
-        mbar_wait(bias_full + par, use & 1);
-        mbar_wait(tmem_full + par, use & 1);
+      if (t1 > t0) {
+        // This row of the user operand (hi half, fp16) goes to tensor memory: lane = row, two values per column,
+        // k-block kb in columns [64 group + 32 kb, +32).  Every MMA that read the previous unit's block completed
+        // before this warp saw the tmem_full of that unit's last accumulator, so the columns are free.
+        const uint4* src = reinterpret_cast<const uint4*>(p.user_split + u * 2 * p.d_pad);
+        for (int kb = 0; kb < n_kb; ++kb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = u_ok ? __ldg(src + kb * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
+            ra[4 * i + 0] = v.x;
+            ra[4 * i + 1] = v.y;
+            ra[4 * i + 2] = v.z;
+            ra[4 * i + 3] = v.w;
+          }
+          tmem_st_32x32b_x32(tmem_lane + group * 64 + kb * (kFKBlock / 2), ra);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + group);
+      }
+
+      float bmax_next = t1 > t0 ? __ldg(p.block_bias_max + t0) : 0.0f;
+      for (int t = t0; t < t1; ++t) {
+        const float bmax_scaled = bmax_next * inv_c;
+        if (t + 1 < t1) bmax_next = __ldg(p.block_bias_max + t + 1);   // in flight while this tile is filtered
+        mbar_wait(tmem_full + slot, slot_use & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (par * 2 + group) * kFBlockN;
-        const uint32_t bias_base = smem_u32(smem + L.bias_off) + par * kFBiasBytes;
+        const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
-        const float bmax_scaled = __ldg(p.block_bias_max + t) * inv_c;
-        uint32_t ra[32], rb[32];
         if (p.debug_mode == 2 || p.debug_mode == 6) goto drained;
-        if (p.debug_mode == 1 || p.debug_mode == 5) {   // 5: drain only, no MMA work either
+        if (p.debug_mode == 1) {
           float acc_dbg = 0.0f;
           for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
             tmem_ld_32x32b_x32(taddr + ch * 32, ra);
@@ -459,37 +475,23 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_
 #pragma unroll 1
         for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
-          if (kVote == 32) {
-            filter_32(ra, bias_base + ch * 32 * 4, pos0 + ch * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c,
-                      ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, pos0 + ch * 32 + h * 16, p.item_perm,
-                        p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
-                        lane, p.k);
-          }
+          filter_32(ra, p.item_bias, pos0 + ch * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau,
+                    theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          if (kVote == 32) {
-            filter_32(rb, bias_base + (ch + 1) * 32 * 4, pos0 + (ch + 1) * 32, p.item_perm, p.item_id_offset,
-                      bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, pos0 + (ch + 1) * 32 + h * 16,
-                        p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3,
-                        buf_row_addr, cnt, lane, p.k);
-          }
+          filter_32(rb, p.item_bias, pos0 + (ch + 1) * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias,
+                    tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
           tmem_ld_wait();
         }
       drained:
         // accumulator and bias slot drained
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(tmem_empty + par);
-          mbar_arrive(bias_empty + par);
+        if (lane == 0) mbar_arrive(tmem_empty + slot);
+        slot += 2;                          // q += 2
+        if (slot >= kFAccSlots) {
+          slot -= kFAccSlots;
+          ++slot_use;
         }
       }
 
@@ -783,14 +785,14 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, bias_base + (ch * 32 + h * 16) * 4, pos0 + ch * 32 + h * 16, p.item_perm,
+            filter_16(ra + h * 16, p.item_bias, pos0 + ch * 32 + h * 16, p.item_perm,
                       p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
                       p.k);
           tmem_ld_wait();
           if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, bias_base + ((ch + 1) * 32 + h * 16) * 4, pos0 + (ch + 1) * 32 + h * 16, p.item_perm,
+            filter_16(rb + h * 16, p.item_bias, pos0 + (ch + 1) * 32 + h * 16, p.item_perm,
                       p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
                       p.k);
           tmem_ld_wait();
@@ -998,6 +1000,8 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
                 "score_filter: operands must be 16-byte aligned");
 
   FilterParams p;
+  p.user_split = static_cast<const __half*>(user_split);
+  p.d_pad = d_pad;
   p.user_scale = user_scale;
   p.user_bias = user_bias;
   p.user_norm = user_norm;
@@ -1068,21 +1072,20 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
 
   p.n_stages = 0;
   for (int s = kFMaxStages; s >= 2; --s)
-    if (filter_layout(p.n_kblocks, s).total + 1024 <= kFSmemLimit) {
+    if (s % p.n_kblocks == 0 && filter_layout(s).total + 1024 <= kFSmemLimit) {
       p.n_stages = s;
       break;
     }
-  TRK_CHECK_ARG(p.n_stages >= 2, "score_filter: shared memory budget exceeded");
+  TRK_CHECK_ARG(p.n_stages >= 2 * p.n_kblocks, "score_filter: shared memory budget exceeded");
   rc = make_hi_map(&map_items, item_hi, n_items, d_pad, d_pad, kFBlockN);
   if (rc != TRK_OK) return rc;
 
-  const uint32_t smem_bytes = filter_layout(p.n_kblocks, p.n_stages).total + 1024;
-  const char* vote = getenv("TRK_FILTER_VOTE");
-  auto kernel = (vote != nullptr && atoi(vote) == 16) ? score_filter_kernel<16> : score_filter_kernel<32>;
+  const uint32_t smem_bytes = filter_layout(p.n_stages).total + 1024;
+  auto kernel = p.n_kblocks == 2 ? score_filter_kernel<2> : score_filter_kernel<1>;
   TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
   const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
-  kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_users, map_items, p);
+  kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_items, p);
   TRK_CHECK_LAUNCH();
   if (p.debug_mode != 0) {   // timing experiments only: report the SM clock CTA 0 saw (synchronises)
     long long clk[2] = {0, 0};
