@@ -126,17 +126,40 @@ __device__ __forceinline__ bool cand_before(float xs, int32_t xi, float ys, int3
   return xs > ys || (xs == ys && xi < yi);
 }
 
+// Inputs of the admission path that are the same for the whole kernel.
+struct AdmitCtx {
+  const float* bias;     // item biases in processing order, padded with -inf
+  const int32_t* perm;   // processing position -> local item index, or null = identity
+  int32_t id_offset;
+  int32_t n_items;
+};
+
 // Warp-cooperative compaction of the candidate buffer of lane `src`'s row: one entry per lane, bitonic sort by
 // (score desc, id asc), keep everything >= k-th best - 2.25m (at most kKeepMax), tighten that row's thresholds.
-__device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int src, int k, int& cnt, float& theta,
-                                            float& tau, float& drop_max, float m3, float ubias, float inv_c) {
+// Entries [n_res, cnt) of the buffer are RAW -- (accumulator value, processing position) exactly as the hot loop
+// found them; they are turned into (approximate score, item id) here, where the bias and permutation lookups of all
+// of them are independent loads issued by different lanes (one L2 latency per compaction, not one per admission).
+__device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int src, int k, int& cnt, int& n_res,
+                                            float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
+                                            float inv_c, const AdmitCtx& ctx) {
   const float kNegInf = -__int_as_float(0x7f800000);
   const int n = __shfl_sync(0xffffffffu, cnt, src);
+  const int nr = __shfl_sync(0xffffffffu, n_res, src);
   const uint32_t addr = __shfl_sync(0xffffffffu, buf_row_addr, src);
   const float m3s = __shfl_sync(0xffffffffu, m3, src);
+  const float cs = __shfl_sync(0xffffffffu, c, src);
+  const float ubs = __shfl_sync(0xffffffffu, ubias, src);
   float s = kNegInf;
   int32_t id = 0x7fffffff;
-  if (lane < n) f_lds64(addr + lane * 8, &s, &id);
+  if (lane < n) {
+    f_lds64(addr + lane * 8, &s, &id);
+    if (lane >= nr) {
+      const int32_t pos = id;
+      const float b = __ldg(ctx.bias + pos);
+      id = pos < ctx.n_items ? ctx.id_offset + (ctx.perm != nullptr ? __ldg(ctx.perm + pos) : pos) : 0x7fffffff;
+      s = fmaf(s, cs, ubs) + b;   // approximate score: (acc * c + user bias) + item bias
+    }
+  }
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -169,6 +192,7 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   if (lane < n_keep) f_sts64(addr + lane * 8, s, id);
   if (lane == src) {
     cnt = n_keep;
+    n_res = n_keep;
     if (ovf) drop_max = fmaxf(drop_max, first_dropped);
     if (have_k) {
       theta = floor_s;
@@ -198,22 +222,20 @@ __device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
   return amax;
 }
 
-// slow path of 16 columns: the lanes whose bound passed form the exact v_j and append their survivors, then rows
-// whose buffer passed half full are compacted by the whole warp.  Called warp-uniformly.
-__device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, const float* __restrict__ bias, int32_t pos_base,
-                                         const int32_t* __restrict__ perm, int32_t id_offset, float c, float inv_c,
-                                         float ubias, float& tau, float& theta, float& drop_max, float m3,
-                                         uint32_t buf_row_addr, int& cnt, int lane, int k) {
+// slow path of 16 columns: the lanes whose bound passed append every column that passes the same bound as a raw
+// (accumulator, position) entry -- a superset of the exact test acc_j + bias_j / c > tau, since bias_j <= block max and
+// rounding is monotonic; no memory is read here.  Rows whose buffer passed half full are then compacted by the whole
+// warp.  Called warp-uniformly.
+__device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t pos_base, float bmax_scaled,
+                                         const AdmitCtx& ctx, float c, float inv_c, float ubias, float& tau,
+                                         float& theta, float& drop_max, float m3, uint32_t buf_row_addr, int& cnt,
+                                         int& n_res, int lane, int k) {
   if (hit) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float b = __ldg(bias + pos_base + j);   // rare path: the padded, processing-order bias array (L2 resident)
-      const float v = fmaf(b, inv_c, __uint_as_float(acc[j]));
-      if (v > tau) {
-        const float a = fmaf(__uint_as_float(acc[j]), c, ubias) + b;   // approximate score
+      if (__uint_as_float(acc[j]) + bmax_scaled > tau) {
         if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
-          const int32_t pos = pos_base + j;
-          f_sts64(buf_row_addr + cnt * 8, a, id_offset + (perm != nullptr ? __ldg(perm + pos) : pos));
+          f_sts64(buf_row_addr + cnt * 8, __uint_as_float(acc[j]), pos_base + j);
           cnt += 1;
         }
       }
@@ -224,33 +246,33 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, const fl
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
-    compact_row(buf_row_addr, lane, src, k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
+    compact_row(buf_row_addr, lane, src, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
   }
 }
 
-__device__ __forceinline__ void filter_16(const uint32_t* acc, const float* __restrict__ bias, int32_t pos_base,
-                                          const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
+__device__ __forceinline__ void filter_16(const uint32_t* acc, int32_t pos_base, float bmax_scaled, const AdmitCtx& ctx,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
-                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
+                                          int lane, int k) {
   // inv_c is a power of two: bmax_scaled is exact and fl(amax + bmax_scaled) >= fl(acc_j + bias_j * inv_c) for all j
   const bool hit = acc_max_16(acc) + bmax_scaled > tau;
   if (__any_sync(0xffffffffu, hit))
-    admit_16(acc, hit, bias, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
+    admit_16(acc, hit, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, n_res,
              lane, k);
 }
 
 // 32 columns behind ONE vote (the two 16-column maxima are independent chains); the slow path still admits in
 // 16-column steps so that the 32-entry buffer cannot overflow between compactions.
-__device__ __forceinline__ void filter_32(const uint32_t* acc, const float* __restrict__ bias, int32_t pos_base,
-                                          const int32_t* __restrict__ perm, int32_t id_offset, float bmax_scaled,
+__device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base, float bmax_scaled, const AdmitCtx& ctx,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
-                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int lane, int k) {
+                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
+                                          int lane, int k) {
   const float a0 = acc_max_16(acc), a1 = acc_max_16(acc + 16);
   if (__any_sync(0xffffffffu, fmaxf(a0, a1) + bmax_scaled > tau)) {
-    admit_16(acc, a0 + bmax_scaled > tau, bias, pos_base, perm, id_offset, c, inv_c, ubias, tau, theta, drop_max, m3,
-             buf_row_addr, cnt, lane, k);
-    admit_16(acc + 16, a1 + bmax_scaled > tau, bias, pos_base + 16, perm, id_offset, c, inv_c, ubias, tau, theta,
-             drop_max, m3, buf_row_addr, cnt, lane, k);
+    admit_16(acc, a0 + bmax_scaled > tau, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3,
+             buf_row_addr, cnt, n_res, lane, k);
+    admit_16(acc + 16, a1 + bmax_scaled > tau, pos_base + 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max,
+             m3, buf_row_addr, cnt, n_res, lane, k);
   }
 }
 
@@ -404,6 +426,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
     const float max_item_norm = __ldg(p.item_stats + 0);
     const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
     const float max_item_bias = __ldg(p.item_stats + 2);
+    const AdmitCtx ctx = {p.item_bias, p.item_perm, p.item_id_offset, static_cast<int32_t>(p.n_items)};
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t slot = group, slot_use = 0;   // accumulator number q = 2 (tile count) + group: slot q % 3, use q / 3
 
@@ -422,7 +445,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       // error bound of one approximate score: operand rounding + the fp32 rounding of the two bias adds
       const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
       float tau = p.debug_mode == 4 ? -kNegInf : kNegInf, theta = kNegInf;   // 4: timing experiment, nothing admitted
-      int cnt = 0;
+      int cnt = 0, n_res = 0;
       float drop_max = kNegInf;
       uint32_t ra[32], rb[32];
 
@@ -475,12 +498,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
 #pragma unroll 1
         for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
-          filter_32(ra, p.item_bias, pos0 + ch * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau,
-                    theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          filter_32(ra, pos0 + ch * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
+                    n_res, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          filter_32(rb, p.item_bias, pos0 + (ch + 1) * 32, p.item_perm, p.item_id_offset, bmax_scaled, c, inv_c, ubias,
-                    tau, theta, drop_max, m3, buf_row_addr, cnt, lane, p.k);
+          filter_32(rb, pos0 + (ch + 1) * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
+                    cnt, n_res, lane, p.k);
           tmem_ld_wait();
         }
       drained:
@@ -497,7 +520,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
 
       // end of the item range: final compaction of every row of this warp, then emit the survivors
       for (int src = 0; src < 32; ++src)
-        compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
+        compact_row(buf_row_addr, lane, src, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
       if (u_ok) {
         const int64_t base = (u * p.n_splits + sp) * 2;   // list 0 of 2; list 1 is left empty (pair form fills both)
         float* os = p.cand_score + base * kKeepMax;
@@ -722,6 +745,7 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
     const float max_item_norm = __ldg(p.item_stats + 0);
     const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
     const float max_item_bias = __ldg(p.item_stats + 2);
+    const AdmitCtx ctx = {p.item_bias, p.item_perm, p.item_id_offset, static_cast<int32_t>(p.n_items)};
     uint32_t it = 0;
     int32_t epoch = 0;
 
@@ -739,7 +763,7 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
       const float inv_c = 1.0f / c;
       const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
       float tau = kNegInf, theta = kNegInf, theta_seen = kNegInf, drop_max = kNegInf;
-      int cnt = 0;
+      int cnt = 0, n_res = 0;
       epoch += 1;                                        // thresholds of the previous work item must not be used
       f_sts64(theta_mine, kNegInf, epoch);
 
@@ -785,16 +809,14 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, p.item_bias, pos0 + ch * 32 + h * 16, p.item_perm,
-                      p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
-                      p.k);
+            filter_16(ra + h * 16, pos0 + ch * 32 + h * 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3,
+                      buf_row_addr, cnt, n_res, lane, p.k);
           tmem_ld_wait();
           if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, p.item_bias, pos0 + (ch + 1) * 32 + h * 16, p.item_perm,
-                      p.item_id_offset, bmax_scaled, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, lane,
-                      p.k);
+            filter_16(rb + h * 16, pos0 + (ch + 1) * 32 + h * 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max,
+                      m3, buf_row_addr, cnt, n_res, lane, p.k);
           tmem_ld_wait();
         }
         if (theta > theta_before) f_sts64(theta_mine, theta, epoch);   // publish the tightened threshold
@@ -808,7 +830,7 @@ score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __
       }
 
       for (int src = 0; src < 32; ++src)
-        compact_row(buf_row_addr, lane, src, p.k, cnt, theta, tau, drop_max, m3, ubias, inv_c);
+        compact_row(buf_row_addr, lane, src, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
       if (u_ok) {
         const int64_t base = (u * p.n_splits + sp) * 2 + group;
         float* os = p.cand_score + base * kKeepMax;
