@@ -161,17 +161,16 @@ int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const 
  *                          power-of-two factors; perm NULL = identity)
  *   trk_pack_item_bias     out[p] = bias[perm[p]], padded with -inf to n_padded (multiple of 256) entries; stats[2] =
  *                          max |bias|; block_max[b] = max bias of positions [128 b, 128 b + 128)
- * Processing order: the host sorts the items by bias (perm = stable argsort) so that the biases inside a 128-item
- * block are nearly equal; the kernel's hot loop then bounds acc_j + bias_j / c by max_j acc_j + block_max / c and
- * touches neither the biases nor an FFMA per score.  Candidate ids are reported in ORIGINAL numbering.
- * Filter outputs, two lists per (user, split): cand_* [n_users, n_splits, 2, 16] (approximate score, global id;
- * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits, 2].
- * Two launch forms: one CTA per 256 users (default) or, with TRK_FILTER_FORM=pair, clusters of two CTAs driving
- * tcgen05 cta_group::2 MMAs (M = 256 across two SMs).
+ * Processing order: the host sorts the items by DESCENDING bias (perm = stable argsort) so that the biases inside a
+ * 128-item block are nearly equal and the running k-th best rises early; the kernel's hot loop then bounds
+ * acc_j + bias_j / c by max_j acc_j + block_max / c and touches neither the biases nor an FFMA per score.  Candidate
+ * ids are reported in ORIGINAL numbering.
+ * Filter outputs, one list per (user, split): cand_* [n_users, n_splits, 16] (approximate score, global id;
+ * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits].
  * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_filter_max_k(); n_components <= 128 for the rescoring.
  * ---------------------------------------------------------------------------------------------------- */
 int trk_score_filter_max_k(void);
-int trk_score_filter_list_width(void); /* candidates per list: 16 (two lists per (user, split)) */
+int trk_score_filter_list_width(void); /* candidates per list: 16 (one list per (user, split)) */
 int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm,
                       float* stats, void* stream);
 int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, const int32_t* perm,
@@ -184,7 +183,7 @@ int trk_score_filter_f16(const void* user_split, const float* user_scale, const 
                          int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
                          int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
                          int32_t* row_flags, void* stream);
-/* item_repr holds the rows of THIS shard: global id g lives at row g - item_id_offset.  n_lists = 2 * n_splits,
+/* item_repr holds the rows of THIS shard: global id g lives at row g - item_id_offset.  n_lists = n_splits,
  * list_width = 16.  out_flag[u] = 1 -> re-run user u through the exact kernel. */
 int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,
                          const float* item_bias, const int32_t* cand_item, const float* row_theta,

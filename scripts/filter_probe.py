@@ -46,24 +46,18 @@ def timeit(fn, n=3):
 
 
 pairs = A.users * float(A.items)
-os.environ['TRK_FILTER_FORM'] = 'single'
 ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
-print('filter single-CTA form: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
 for mode in ('7', '4', '1', '2', '6'):
     os.environ['TRK_FILTER_DEBUG'] = mode
     ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
-    print('single form debug=%s: %.2f ms' % (mode, ms))
-os.environ['TRK_FILTER_DEBUG'] = '0'
-os.environ['TRK_FILTER_FORM'] = 'pair'
-for mode in (('0', '1', '2') if os.environ.get('PROBE_PAIR') else ()):
-    os.environ['TRK_FILTER_DEBUG'] = mode
-    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
-    print('filter debug=%s: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (mode, ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+    print('filter debug=%s: %.2f ms' % (mode, ms))
 os.environ['TRK_FILTER_DEBUG'] = '0'
 ms = timeit(lambda: kernels.score_topk(us, usc, ub, its, meta, A.users, A.items, d_pad, A.k))
 print('exact top-k (3 pass): %.2f ms  %.3e pairs/s  issued %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 6 * pairs * A.d / ms / 1e9))
-ms = timeit(lambda: kernels.rescore_topk(u32, i32, ub, ib, kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k)[1], *kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k)[2:], unorm, stats, A.k), n=1)
-print('2x filter + rescore: %.2f ms' % ms)
+cs, ci, theta, flags = kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k)
+ms = timeit(lambda: kernels.rescore_topk(u32, i32, ub, ib, ci, theta, flags, unorm, stats, A.k))
+print('rescore_topk: %.2f ms' % ms)
 nu = min(A.users, 32768)
 out = torch.empty((nu, A.items), dtype=torch.float32, device=dev)
 ms = timeit(lambda: kernels.score_dense_tc(us[:nu], usc[:nu], ub[:nu], its, meta, nu, A.items, d_pad, out=out))

@@ -6,28 +6,31 @@
 // (tensorrec/prediction_graphs.py:49-50), bias_prediction_dense (tensorrec/recommendation_graphs.py:41),
 // rank_predictions (:73-82) restricted to rank <= k.
 //
-// CTA = 256 user rows (two 128-row blocks A0, A1 resident in shared memory) x a sweep over 128-item tiles: every B tile
-// fetched from L2 feeds two MMAs.  (Measured, scripts/filter_probe.py: with one user block per CTA the kernel is bound
-// by the L2->SM stream of the item operand, 5.7 TB/s, not by the tensor pipe.)  Epilogue group g = warps 4+4g..7+4g
-// drains user block g: one thread per user row, two 128-column accumulators per block (4 x 128 = all 512 TMEM
-// columns) so the MMA warp fills one while the group drains the other.
+// CTA = 256 user rows (two 128-row blocks) x a sweep over 128-item tiles: every B tile fetched from L2 feeds two
+// accumulators.  The user rows live in TENSOR MEMORY (columns [0,128), written by the epilogue threads with
+// tcgen05.st) and are the A operand of tcgen05.mma straight from there; the remaining 384 columns hold a ring of
+// three 128-column accumulators.  Epilogue group g = warps 4+4g..7+4g drains the accumulators of user block g, one
+// thread per user row.
 //
 // Why: the exact split-product kernel issues 3 tensor passes and its per-row sorted-list inserts serialise a warp
 // (profiles/r1_v2_fused_ncu.json: tensor pipe 37 %, top stall = insert loop).  Here
 //   * tensor work is 1 pass (2*U*I*d flops = the algorithmic count);
-//   * the epilogue hot loop is 1 FFMA + 1/2 FMNMX3 per score: v_j = acc_j + bias_j / c  against a per-row threshold
-//     tau (c = user scale x GLOBAL item scale, both powers of two), branch per 16 columns;
-//   * a passing column is APPENDED (unsorted) to the row's 32-entry buffer in shared memory -- a handful of
-//     instructions; when some row's buffer passes half full the whole warp compacts it cooperatively: one entry per
-//     lane, a 15-step bitonic sort through shuffles, keep everything >= (k-th best - 2.25m), tighten the threshold;
-//   * item biases come through a small TMA-fed ring with their own mbarriers: the epilogue warps never meet at a
-//     block or group barrier.
+//   * items are processed in descending-bias order (host side), so within a 128-item block the biases are almost equal
+//     and the admission test v_j = acc_j + bias_j / c > tau (c = user scale x GLOBAL item scale, both powers of two)
+//     is bounded by max_j acc_j + blockmax / c: the hot loop is an FMNMX3 tree over the raw accumulators, one add and
+//     one warp vote per 32 columns;
+//   * a passing column is APPENDED raw (accumulator, position) to the row's 32-entry buffer in shared memory; when
+//     some row's buffer passes half full the whole warp compacts it cooperatively: one entry per lane, raw entries
+//     resolved to (approximate score, item id), a 15-step bitonic sort through shuffles, keep everything >= (k-th best
+//     - 2.25m), tighten the threshold;
+//   * the epilogue warps never meet at a block or group barrier.
 //
 // Error bound.  hi = fp16(x * 2^e) has relative error <= 2^-11 per element (absolute 2^-25 below the fp16 normal
 // range), so |approx - exact| <= (2^-10 + 2^-22) |u|.|i| <= m := kMarginFactor * |u|_2 * max_j |i_j|_2 with
 // kMarginFactor = 1.5 * 2^-10 (covers the fp32 accumulation of the tensor core and the flush of tiny elements).
 // Every item ever excluded had approx <= theta_final, hence exact <= theta_final + m, and theta = a_k - 2.25m keeps
-// theta + m strictly below the exact k-th best of the survivors (which is >= a_k - m).  rescore_topk_kernel checks exactly that inequality.
+// theta + m strictly below the exact k-th best of the survivors (which is >= a_k - m).  rescore_topk_kernel checks
+// exactly that inequality.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -41,7 +44,6 @@ constexpr uint32_t kFTmemAccCol = 128;   // first accumulator column (columns [0
 constexpr int kFKBlock = 64;
 constexpr int kFUmmaK = 16;
 constexpr int kFThreads = 384;
-constexpr uint32_t kFATileBytes = kFBlockM * kFKBlock * 2;   // 16 KB
 constexpr uint32_t kFBTileBytes = kFBlockN * kFKBlock * 2;   // 16 KB
 constexpr int kFMaxStages = 10;
 constexpr uint32_t kFTmemCols = 512;
@@ -74,10 +76,10 @@ struct FilterParams {
   int32_t item_id_offset;
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
-  float* cand_score;           // [n_users, n_splits, 2, kKeepMax] approximate scores (sentinel -inf)
-  int32_t* cand_item;          // [n_users, n_splits, 2, kKeepMax] global ids (sentinel INT32_MAX)
-  float* row_theta;            // [n_users, n_splits, 2] final admission threshold
-  int32_t* row_flags;          // [n_users, n_splits, 2] reserved (0); certification happens in rescore_topk_kernel
+  float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
+  int32_t* cand_item;          // [n_users, n_splits, kKeepMax] global ids (sentinel INT32_MAX)
+  float* row_theta;            // [n_users, n_splits] final admission threshold
+  int32_t* row_flags;          // [n_users, n_splits] reserved (0); certification happens in rescore_topk_kernel
 };
 
 struct FilterLayout {
@@ -224,41 +226,34 @@ __device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
 
 // slow path of 16 columns: the lanes whose bound passed append every column that passes the same bound as a raw
 // (accumulator, position) entry -- a superset of the exact test acc_j + bias_j / c > tau, since bias_j <= block max and
-// rounding is monotonic; no memory is read here.  Rows whose buffer passed half full are then compacted by the whole
-// warp.  Called warp-uniformly.
+// rounding is monotonic; no memory is read here.  A row is compacted (by the whole warp) only when its buffer could not
+// take the new entries: ~4 compactions per user at 1M items instead of 9 with a "more than half full" trigger.
+// Called warp-uniformly.
 __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t pos_base, float bmax_scaled,
                                          const AdmitCtx& ctx, float c, float inv_c, float ubias, float& tau,
                                          float& theta, float& drop_max, float m3, uint32_t buf_row_addr, int& cnt,
                                          int& n_res, int lane, int k) {
+  uint32_t pass = 0;
   if (hit) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (__uint_as_float(acc[j]) + bmax_scaled > tau) {
-        if (cnt < kBufEntries) {   // invariant: cnt <= 16 on entry, so this always holds
-          f_sts64(buf_row_addr + cnt * 8, __uint_as_float(acc[j]), pos_base + j);
-          cnt += 1;
-        }
-      }
-    }
+    for (int j = 0; j < 16; ++j) pass |= (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
   }
-  __syncwarp();
-  unsigned need = __ballot_sync(0xffffffffu, cnt > kBufEntries - 16);
+  __syncwarp();   // earlier appends of every lane are visible to the lanes that may now compact its row
+  unsigned need = __ballot_sync(0xffffffffu, cnt + __popc(pass) > kBufEntries);
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
     compact_row(buf_row_addr, lane, src, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
   }
-}
-
-__device__ __forceinline__ void filter_16(const uint32_t* acc, int32_t pos_base, float bmax_scaled, const AdmitCtx& ctx,
-                                          float c, float inv_c, float ubias, float& tau, float& theta,
-                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
-                                          int lane, int k) {
-  // inv_c is a power of two: bmax_scaled is exact and fl(amax + bmax_scaled) >= fl(acc_j + bias_j * inv_c) for all j
-  const bool hit = acc_max_16(acc) + bmax_scaled > tau;
-  if (__any_sync(0xffffffffu, hit))
-    admit_16(acc, hit, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, n_res,
-             lane, k);
+  if (pass != 0) {   // cnt + popc(pass) <= kBufEntries holds here (a compaction leaves at most kKeepMax = 16)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if ((pass >> j) & 1u) {
+        f_sts64(buf_row_addr + cnt * 8, __uint_as_float(acc[j]), pos_base + j);
+        cnt += 1;
+      }
+    }
+  }
 }
 
 // 32 columns behind ONE vote (the two 16-column maxima are independent chains); the slow path still admits in
@@ -522,7 +517,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       for (int src = 0; src < 32; ++src)
         compact_row(buf_row_addr, lane, src, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
       if (u_ok) {
-        const int64_t base = (u * p.n_splits + sp) * 2;   // list 0 of 2; list 1 is left empty (pair form fills both)
+        const int64_t base = u * p.n_splits + sp;
         float* os = p.cand_score + base * kKeepMax;
         int32_t* oi = p.cand_item + base * kKeepMax;
         for (int e = 0; e < kKeepMax; ++e) {
@@ -534,12 +529,6 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         }
         p.row_theta[base] = fmaxf(theta, drop_max);   // every excluded item has an approximate score <= this
         p.row_flags[base] = 0;
-        for (int e = 0; e < kKeepMax; ++e) {
-          os[kKeepMax + e] = kNegInf;
-          oi[kKeepMax + e] = 0x7fffffff;
-        }
-        p.row_theta[base + 1] = kNegInf;
-        p.row_flags[base + 1] = 0;
       }
       __syncwarp();
     }
@@ -556,305 +545,6 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<kFTmemCols>(tmem_base);
-  }
-}
-
-// =========================================================================================================
-// CTA-pair form (cta_group::2): a cluster of two CTAs works on 256 user rows x 256-item tiles.
-//   * CTA r keeps ITS 128 user rows (A_r) and loads ITS half of every B tile (128 item rows); one thread of the
-//     leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16): per SM the operand read from shared
-//     memory is 4 KB (A) + 4 KB (B half) per 128 cycles = 64 B/clk -- half of the single-CTA N = 128 form, which
-//     sits exactly at the 128 B/clk shared-memory limit (scripts/filter_probe.py: mainloop alone ~50 % of peak);
-//   * each CTA receives the 128 x 256 accumulator of its own rows in its own TMEM (2 x 256 columns, double buffered)
-//     and drains it with 8 epilogue warps: group g takes columns [128 g, 128 g + 128) of every tile, so there are
-//     twice as many epilogue warps per output as in the single-CTA form;
-//   * the two groups keep separate candidate lists per row and publish their thresholds to each other through shared
-//     memory (a threshold derived from ANY k items is a valid exclusion bound for the row);
-//   * barriers: b_full / a_full / tmem_empty live in the leader (TMA of both CTAs completes on the leader's barrier,
-//     the peer's epilogue arrives remotely), b_empty / a_empty / tmem_full are multicast by tcgen05.commit to both.
-// =========================================================================================================
-constexpr int kPThreads = 384;
-constexpr int kPTileN = 256;                                   // items per tile (128 rows of B per CTA)
-constexpr uint32_t kPBHalfBytes = 128 * kFKBlock * 2;          // 16 KB
-constexpr uint32_t kPBiasBytes = kPTileN * 4;                  // 1 KB
-constexpr int kPMaxStages = 8;
-
-struct PairLayout {
-  uint32_t a_off, b_off, buf_off, bias_off, theta_off, bar_off, total;
-};
-__host__ __device__ inline PairLayout pair_layout(int n_kblocks, int n_stages) {
-  PairLayout L;
-  L.a_off = 0;
-  L.b_off = L.a_off + static_cast<uint32_t>(n_kblocks) * kFATileBytes;
-  L.buf_off = L.b_off + static_cast<uint32_t>(n_stages) * kPBHalfBytes;
-  L.bias_off = L.buf_off + 2u * kFBlockM * kBufEntries * 8u;      // 2 groups x 128 rows x 32 entries
-  L.theta_off = L.bias_off + 2u * kPBiasBytes;
-  L.bar_off = L.theta_off + 2u * kFBlockM * 8u;                  // {theta, epoch} per (group, row)
-  L.total = L.bar_off + 512u;
-  return L;
-}
-// barriers (uint64): [0] a_full (leader) [1] a_empty [2..3] tmem_full [4..5] tmem_empty (leader, 16 arrivals)
-// [6..7] bias_full (local) [8..9] bias_empty (local) [10 .. 10+S) b_full (leader) [10+S .. 10+2S) b_empty
-
-__global__ void __launch_bounds__(kPThreads, 1)
-score_filter_pair_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
-                         const FilterParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const PairLayout L = pair_layout(p.n_kblocks, p.n_stages);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
-  uint64_t* a_full = bars + 0;
-  uint64_t* a_empty = bars + 1;
-  uint64_t* tmem_full = bars + 2;
-  uint64_t* tmem_empty = bars + 4;
-  uint64_t* bias_full = bars + 6;
-  uint64_t* bias_empty = bars + 8;
-  uint64_t* b_full = bars + 10;
-  uint64_t* b_empty = bars + 10 + p.n_stages;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem + L.bar_off + 400);
-
-  const int warp = threadIdx.x / 32;
-  const int lane = threadIdx.x % 32;
-  const int n_kb = p.n_kblocks;
-  const uint32_t rank = cluster_ctarank();          // 0 = leader
-  const bool leader = rank == 0;
-  const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * p.n_splits;
-  const int64_t cluster_id = blockIdx.x / 2, n_clusters = gridDim.x / 2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_users);
-    tma_prefetch_desc(&map_items);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 16);     // 8 epilogue warps of each CTA
-      mbar_init(bias_full + i, 1);
-      mbar_init(bias_empty + i, 8);
-    }
-    for (int i = 0; i < p.n_stages; ++i) {
-      mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc_pair<kFTmemCols>(tmem_base_smem);
-  tcgen05_fence_before();
-  cluster_sync_all();                    // barriers of both CTAs are initialised before anyone signals them
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-
-  if (warp == 0) {
-    // ===================================== TMA producer (both CTAs) ==========================
-    uint32_t fill = 0, witer = 0, it = 0;
-    const uint32_t a_full_leader = cluster_map_addr(a_full, 0);
-    for (int64_t w = cluster_id; w < n_work; w += n_clusters) {
-      const int up = static_cast<int>(w % p.n_user_pairs);
-      const int sp = static_cast<int>(w / p.n_user_pairs);
-      const int t0 = sp * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-      if (t1 <= t0) continue;
-      mbar_wait(a_empty, (witer & 1) ^ 1);
-      if (elect_one()) {
-        if (leader) mbar_arrive_expect_tx(a_full, 2 * n_kb * kFATileBytes);   // both CTAs' A blocks
-        for (int kb = 0; kb < n_kb; ++kb)
-          tma_load_2d_pair(smem + L.a_off + kb * kFATileBytes, &map_users, a_full_leader, kb * kFKBlock,
-                           (up * 2 + static_cast<int>(rank)) * kFBlockM, kEvictFirst);
-      }
-      __syncwarp();
-      ++witer;
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t par = it & 1, use = it >> 1;
-        mbar_wait(bias_empty + par, (use & 1) ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bias_full + par, kPBiasBytes);
-          bulk_load_1d(smem + L.bias_off + par * kPBiasBytes, p.item_bias + static_cast<int64_t>(t) * kPTileN,
-                       kPBiasBytes, bias_full + par);
-        }
-        __syncwarp();
-        for (int kb = 0; kb < n_kb; ++kb) {
-          const uint32_t s = fill % p.n_stages;
-          mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
-          if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(b_full + s, 2 * kPBHalfBytes);   // this CTA's half + the peer's half
-            tma_load_2d_pair(smem + L.b_off + s * kPBHalfBytes, &map_items, cluster_map_addr(b_full + s, 0),
-                             kb * kFKBlock, t * kPTileN + static_cast<int>(rank) * 128, kEvictLast);
-          }
-          __syncwarp();
-          ++fill;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer (leader CTA only) ======================
-    if (leader) {
-      constexpr uint32_t idesc = umma_idesc_f16_f32(256, kPTileN);
-      uint32_t fill = 0, witer = 0, it = 0;
-      const uint32_t a_base = smem_u32(smem + L.a_off);
-      const uint32_t b_base = smem_u32(smem + L.b_off);
-      for (int64_t w = cluster_id; w < n_work; w += n_clusters) {
-        const int sp = static_cast<int>(w / p.n_user_pairs);
-        const int t0 = sp * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        if (t1 <= t0) continue;
-        mbar_wait(a_full, witer & 1);
-        ++witer;
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t par = it & 1, use = it >> 1;
-          mbar_wait(tmem_empty + par, (use & 1) ^ 1);   // all 16 epilogue warps of the pair drained this accumulator
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + par * kPTileN;
-          uint32_t accumulate = 0;
-          for (int kb = 0; kb < n_kb; ++kb) {
-            const uint32_t s = fill % p.n_stages;
-            mbar_wait(b_full + s, (fill / p.n_stages) & 1);
-            tcgen05_fence_after();
-            const uint64_t da = umma_desc_k_major_sw128(a_base + kb * kFATileBytes);
-            const uint64_t db = umma_desc_k_major_sw128(b_base + s * kPBHalfBytes);
-            if (elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < kFKBlock / kFUmmaK; ++ks)
-                umma_f16_ss_pair(d_tmem, da + 2u * ks, db + 2u * ks, idesc, accumulate | static_cast<uint32_t>(ks > 0));
-              umma_commit_pair(b_empty + s, 3);      // frees stage s in both CTAs
-            }
-            __syncwarp();
-            accumulate = 1;
-            ++fill;
-          }
-          if (elect_one()) umma_commit_pair(tmem_full + par, 3);
-          __syncwarp();
-        }
-        if (elect_one()) umma_commit_pair(a_empty, 3);
-        __syncwarp();
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================================== epilogue (both CTAs, 8 warps) =====================
-    const int group = (warp - 4) / 4;               // column half of every tile
-    const int quarter = warp % 4;
-    const int row = quarter * 32 + lane;
-    const float kNegInf = -__int_as_float(0x7f800000);
-    const uint32_t buf_row_addr =
-        smem_u32(smem + L.buf_off) + static_cast<uint32_t>((group * kFBlockM + row) * kBufEntries * 8);
-    const uint32_t theta_mine = smem_u32(smem + L.theta_off) + static_cast<uint32_t>((group * kFBlockM + row) * 8);
-    const uint32_t theta_other = smem_u32(smem + L.theta_off) + static_cast<uint32_t>(((1 - group) * kFBlockM + row) * 8);
-    const uint32_t tmem_empty_leader0 = cluster_map_addr(tmem_empty + 0, 0);
-    const uint32_t tmem_empty_leader1 = cluster_map_addr(tmem_empty + 1, 0);
-    const float max_item_norm = __ldg(p.item_stats + 0);
-    const float item_scale = fmaxf(__ldg(p.item_stats + 1), 1e-38f);
-    const float max_item_bias = __ldg(p.item_stats + 2);
-    const AdmitCtx ctx = {p.item_bias, p.item_perm, p.item_id_offset, static_cast<int32_t>(p.n_items)};
-    uint32_t it = 0;
-    int32_t epoch = 0;
-
-    for (int64_t w = cluster_id; w < n_work; w += n_clusters) {
-      const int up = static_cast<int>(w % p.n_user_pairs);
-      const int sp = static_cast<int>(w / p.n_user_pairs);
-      const int t0 = sp * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-      const int64_t u = (static_cast<int64_t>(up) * 2 + rank) * kFBlockM + row;
-      const bool u_ok = u < p.n_users;
-      const float su = u_ok ? __ldg(p.user_scale + u) : 1.0f;
-      const float ubias = (u_ok && p.user_bias != nullptr) ? __ldg(p.user_bias + u) : 0.0f;
-      const float unorm = u_ok ? __ldg(p.user_norm + u) : 0.0f;
-      const float c = su * item_scale;
-      const float inv_c = 1.0f / c;
-      const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
-      float tau = kNegInf, theta = kNegInf, theta_seen = kNegInf, drop_max = kNegInf;
-      int cnt = 0, n_res = 0;
-      epoch += 1;                                        // thresholds of the previous work item must not be used
-      f_sts64(theta_mine, kNegInf, epoch);
-
-      for (int t = t0; t < t1; ++t, ++it) {
-        const uint32_t par = it & 1, use = it >> 1;
-        {   // adopt the other column group's threshold for this row if it is tighter (valid for the whole row)
-          float ot;
-          int32_t oe;
-          f_lds64(theta_other, &ot, &oe);
-          if (oe == epoch && ot > theta_seen) {
-            theta_seen = ot;
-            if (ot > theta) {
-              const float tt = (ot - ubias) * inv_c;
-              tau = fmaxf(tau, tt - 8.0f * 1.1920929e-7f * fabsf(tt) - 1e-30f);
-            }
-          }
-        }
-        mbar_wait(bias_full + par, use & 1);
-        mbar_wait(tmem_full + par, use & 1);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + par * kPTileN + group * 128;
-        const uint32_t bias_base = smem_u32(smem + L.bias_off) + par * kPBiasBytes + group * 128 * 4;
-        const int32_t pos0 = t * kPTileN + group * 128;
-        const float bmax_scaled = __ldg(p.block_bias_max + 2 * t + group) * inv_c;
-        uint32_t ra[32], rb[32];
-        const float theta_before = theta;
-        if (p.debug_mode == 2) goto drained2;
-        if (p.debug_mode == 1) {
-          float acc_dbg = 0.0f;
-          for (int ch = 0; ch < 4; ++ch) {
-            tmem_ld_32x32b_x32(taddr + ch * 32, ra);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc_dbg = fmaxf(acc_dbg, __uint_as_float(ra[j]));
-          }
-          if (acc_dbg == 1.2345e30f) cnt = 1;
-          goto drained2;
-        }
-        tmem_ld_32x32b_x32(taddr, ra);
-        tmem_ld_wait();
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ch += 2) {
-          tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(ra + h * 16, pos0 + ch * 32 + h * 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3,
-                      buf_row_addr, cnt, n_res, lane, p.k);
-          tmem_ld_wait();
-          if (ch + 2 < 4) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            filter_16(rb + h * 16, pos0 + (ch + 1) * 32 + h * 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max,
-                      m3, buf_row_addr, cnt, n_res, lane, p.k);
-          tmem_ld_wait();
-        }
-        if (theta > theta_before) f_sts64(theta_mine, theta, epoch);   // publish the tightened threshold
-      drained2:
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(par == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
-          mbar_arrive(bias_empty + par);
-        }
-      }
-
-      for (int src = 0; src < 32; ++src)
-        compact_row(buf_row_addr, lane, src, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
-      if (u_ok) {
-        const int64_t base = (u * p.n_splits + sp) * 2 + group;
-        float* os = p.cand_score + base * kKeepMax;
-        int32_t* oi = p.cand_item + base * kKeepMax;
-        for (int e = 0; e < kKeepMax; ++e) {
-          float s = kNegInf;
-          int32_t id = 0x7fffffff;
-          if (e < cnt) f_lds64(buf_row_addr + e * 8, &s, &id);
-          os[e] = s;
-          oi[e] = id;
-        }
-        // every item this list excluded had an approximate score <= max(own threshold, adopted threshold, dropped)
-        p.row_theta[base] = fmaxf(fmaxf(theta, theta_seen), drop_max);
-        p.row_flags[base] = 0;
-      }
-      __syncwarp();
-    }
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();                    // nobody may still signal a barrier or read TMEM of an exited CTA
-  if (warp == 2) {
-    tcgen05_fence_after();
-    tmem_dealloc_pair<kFTmemCols>(tmem_base);
   }
 }
 
@@ -969,7 +659,6 @@ constexpr uint32_t kFSmemLimit = 232448;
 
 int score_filter_max_k() { return kFilterMaxK; }
 int score_filter_list_width() { return kKeepMax; }
-int score_filter_lists_per_split() { return 2; }
 
 int operand_stats(const void* split, const float* scale, int64_t rows, int32_t d_pad, float* out_norm, float* stats,
                   cudaStream_t stream) {
@@ -1048,50 +737,8 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     const char* dbg = getenv("TRK_FILTER_DEBUG");
     p.debug_mode = dbg != nullptr ? atoi(dbg) : 0;
   }
-  // Form: "single" (default) = one CTA per 256 users, one candidate list per row; "pair" = clusters of two CTAs
-  // (tcgen05 cta_group::2).  Measured at 1M x 1M x d128 (scripts/filter_probe.py): the pair form has the faster mainloop
-  // (196 ms vs 227 ms without epilogue) but keeps two lists per row, and the epilogue is what bounds both: 350 ms vs 311 ms.
-  const char* form = getenv("TRK_FILTER_FORM");
-  const bool pair_form = form != nullptr && form[0] == 'p';
-
-  CUtensorMap map_users, map_items;
-  int rc = make_hi_map(&map_users, user_split, n_users, 2 * d_pad, d_pad, kFBlockM);
-  if (rc != TRK_OK) return rc;
-
-  if (pair_form) {
-    p.n_tiles = static_cast<int32_t>(ceil_div(n_items, kPTileN));
-    p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
-    p.n_stages = 0;
-    for (int s = kPMaxStages; s >= 2; --s)
-      if (pair_layout(p.n_kblocks, s).total + 1024 <= kFSmemLimit) {
-        p.n_stages = s;
-        break;
-      }
-    TRK_CHECK_ARG(p.n_stages >= 2, "score_filter: shared memory budget exceeded");
-    rc = make_hi_map(&map_items, item_hi, n_items, d_pad, d_pad, 128);   // each CTA loads half a tile
-    if (rc != TRK_OK) return rc;
-    const uint32_t smem_bytes = pair_layout(p.n_kblocks, p.n_stages).total + 1024;
-    TRK_CHECK_CUDA(
-        cudaFuncSetAttribute(score_filter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
-    const int64_t max_clusters = sm_count() / 2;
-    const int n_clusters = static_cast<int>(n_work < max_clusters ? n_work : max_clusters);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(2 * n_clusters));
-    cfg.blockDim = dim3(kPThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TRK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, score_filter_pair_kernel, map_users, map_items, p));
-    return TRK_OK;
-  }
-
+  CUtensorMap map_items;
+  int rc;
   p.n_stages = 0;
   for (int s = kFMaxStages; s >= 2; --s)
     if (s % p.n_kblocks == 0 && filter_layout(s).total + 1024 <= kFSmemLimit) {

@@ -305,11 +305,11 @@ def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_sta
     if n_splits is None:
         n_splits = default_splits(n_users, n_items)
     dev = user_split.device
-    width = filter_list_width()      # two lists of `width` candidates per (user, split)
-    cand_s = torch.empty((n_users, n_splits, 2, width), dtype=torch.float32, device=dev)
-    cand_i = torch.empty((n_users, n_splits, 2, width), dtype=torch.int32, device=dev)
-    theta = torch.empty((n_users, n_splits, 2), dtype=torch.float32, device=dev)
-    flags = torch.empty((n_users, n_splits, 2), dtype=torch.int32, device=dev)
+    width = filter_list_width()      # one list of `width` candidates per (user, split)
+    cand_s = torch.empty((n_users, n_splits, width), dtype=torch.float32, device=dev)
+    cand_i = torch.empty((n_users, n_splits, width), dtype=torch.int32, device=dev)
+    theta = torch.empty((n_users, n_splits), dtype=torch.float32, device=dev)
+    flags = torch.empty((n_users, n_splits), dtype=torch.int32, device=dev)
     rc = lib.trk_score_filter_f16(_p(user_split), _p(user_scale), _p(user_bias), _p(user_norm), _p(item_hi),
                                   _p(item_stats), _p(item_bias_pad), _p(block_bias_max), _p(item_perm), n_users,
                                   n_items, int(d_pad), int(k),
