@@ -176,7 +176,7 @@ __device__ __forceinline__ void store_chunk_tma(const uint32_t (&r)[32], uint32_
   }
 }
 
-template <bool kDense>
+template <bool kDense, int kNKB>   // kNKB = d_pad / 64 k-blocks per operand half
 __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_constant__ CUtensorMap map_items,
                 const __grid_constant__ CUtensorMap map_out, const TcParams p) {
@@ -197,7 +197,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
-  const int n_kb2 = 2 * p.n_kblocks;
+  constexpr int n_kb2 = 2 * kNKB;
   const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * p.n_splits;
 
   if (warp == 0 && lane == 0) {
@@ -228,7 +228,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   if (warp == 0) {
     // ===================================== TMA producer ======================================
     {   // warp-uniform control flow, one elected lane issues (see the MMA warp)
-      uint32_t fill = 0;   // B stages filled so far
+      int stage = 0;       // B ring position
+      uint32_t stage_phase = 0;
       uint32_t witer = 0;  // non-empty work items so far
       uint32_t it = 0;     // tiles issued so far
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -256,16 +257,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
                          kMetaBytes, meta_full + slot);
           }
           __syncwarp();
+#pragma unroll
           for (int kb = 0; kb < n_kb2; ++kb) {
-            const uint32_t s = fill % p.n_stages;
-            mbar_wait(b_empty + s, ((fill / p.n_stages) & 1) ^ 1);
+            mbar_wait(b_empty + stage, stage_phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(b_full + s, kBTileBytes);
-              tma_load_2d(smem + L.b_off + s * kBTileBytes, &map_items, b_full + s, kb * kKBlock, t * kBlockN,
+              mbar_arrive_expect_tx(b_full + stage, kBTileBytes);
+              tma_load_2d(smem + L.b_off + stage * kBTileBytes, &map_items, b_full + stage, kb * kKBlock, t * kBlockN,
                           kEvictLast);  // the item operand is re-read by every user block: keep it in L2
             }
             __syncwarp();
-            ++fill;
+            if (++stage == p.n_stages) {   // ring position advances incrementally: no div/mod on the issue path
+              stage = 0;
+              stage_phase ^= 1;
+            }
           }
         }
       }
@@ -277,7 +281,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     // instructions per MMA) because it cannot prove the operands uniform.
     {
       constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, kBlockN);
-      uint32_t fill = 0, witer = 0, it = 0;  // it = accumulator tiles produced so far
+      int stage = 0;
+      uint32_t stage_phase = 0, witer = 0, it = 0;  // it = accumulator tiles produced so far
       const uint32_t a_base = smem_u32(smem + L.a_off);
       const uint32_t b_base = smem_u32(smem + L.b_off);
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -292,33 +297,37 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
           mbar_wait(tmem_empty + buf, ((use >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kBlockN;
-          uint32_t accumulate = 0;
+          // One thread issues every MMA of the SM and a k-block is only 4-8 MMA steps: the loop is unrolled over the
+          // (compile-time) k-blocks and the ring position advances incrementally -- `fill % n_stages` with a runtime
+          // stage count cost ~25 dependent instructions (I2F / MUFU.RCP / F2I) in front of every k-block and kept the
+          // tensor pipe at half rate (the same finding as in score_filter_tc.cu).
+#pragma unroll
           for (int kb2 = 0; kb2 < n_kb2; ++kb2) {
-            const uint32_t s = fill % p.n_stages;
-            mbar_wait(b_full + s, (fill / p.n_stages) & 1);
+            mbar_wait(b_full + stage, stage_phase);
             tcgen05_fence_after();
-            const uint32_t b_addr = b_base + s * kBTileBytes;
-            const bool b_is_hi = kb2 < p.n_kblocks;
-            const int kb = b_is_hi ? kb2 : kb2 - p.n_kblocks;
+            const uint64_t db = umma_desc_k_major_sw128(b_base + stage * kBTileBytes);
+            constexpr int kNKBc = kNKB;
+            const bool b_is_hi = kb2 < kNKBc;
+            const int kb = b_is_hi ? kb2 : kb2 - kNKBc;
             // B hi block: A_hi[kb] x B and A_lo[kb] x B ;  B lo block: A_hi[kb] x B
-            const int n_a = b_is_hi ? 2 : 1;
             if (elect_one()) {
-              for (int a = 0; a < n_a; ++a) {
-                const uint32_t a_addr = a_base + (a == 0 ? kb : p.n_kblocks + kb) * kATileBytes;
-                const uint64_t da = umma_desc_k_major_sw128(a_addr);
-                const uint64_t db = umma_desc_k_major_sw128(b_addr);
+#pragma unroll
+              for (int a = 0; a < (b_is_hi ? 2 : 1); ++a) {
+                const uint64_t da = umma_desc_k_major_sw128(a_base + (a == 0 ? kb : kNKBc + kb) * kATileBytes);
 #pragma unroll
                 for (int ks = 0; ks < kKBlock / kUmmaK; ++ks) {
                   // advancing 16 fp16 (32 bytes) inside the 128-byte swizzle atom = +2 in the address field
                   umma_f16_ss(d_tmem, da + 2u * ks, db + 2u * ks, idesc,
-                              (accumulate | static_cast<uint32_t>(a > 0 || ks > 0)));
+                              static_cast<uint32_t>(kb2 > 0 || a > 0 || ks > 0));
                 }
               }
-              umma_commit(b_empty + s);  // stage reusable once these MMAs have read it
+              umma_commit(b_empty + stage);  // stage reusable once these MMAs have read it
             }
             __syncwarp();
-            accumulate = 1;
-            ++fill;
+            if (++stage == p.n_stages) {
+              stage = 0;
+              stage_phase ^= 1;
+            }
           }
           if (elect_one()) umma_commit(tmem_full + buf);  // accumulator complete
           __syncwarp();
@@ -563,7 +572,7 @@ static int launch_tc(const void* user_split, const float* user_scale, const floa
     }
   }
   const uint32_t smem_bytes = make_layout(p.n_kblocks, p.n_stages, p.k, p.tma_store != 0).total + 1024;
-  auto kernel = score_tc_kernel<kDense>;
+  auto kernel = p.n_kblocks == 2 ? score_tc_kernel<kDense, 2> : score_tc_kernel<kDense, 1>;
   TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * n_splits;
   const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
