@@ -48,6 +48,11 @@ def timeit(fn, n=3):
 pairs = A.users * float(A.items)
 ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+for cl in ('1', '2'):
+    os.environ['TRK_FILTER_CLUSTER'] = cl
+    ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))
+    print('filter kernel, clusters of %s: %.2f ms' % (cl, ms))
+os.environ.pop('TRK_FILTER_CLUSTER')
 for mode in ('7', '4', '1', '2', '6'):
     os.environ['TRK_FILTER_DEBUG'] = mode
     ms = timeit(lambda: kernels.score_filter(us, usc, ub, unorm, hi, stats, bias_pad, bmax, perm, A.users, A.items, d_pad, A.k))

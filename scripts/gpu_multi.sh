@@ -1,12 +1,13 @@
 #!/bin/bash
-# usage (under gpurun --gpus N): bash scripts/gpu_multi.sh <tag> <N>
+# usage (under gpurun --gpus N): bash scripts/gpu_multi.sh <tag> <N> [counts]   (counts default "1 N", e.g. "8" or "2 4 8")
 TAG=${1:-rX}
 N=${2:-2}
+COUNTS=${3:-"1 $N"}
 cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 600 python -m pytest tests/test_distributed_gpu.py -m gpu -q -x 2>&1 | tail -5
-for n in 1 $N; do
+for n in $COUNTS; do
   if [ "$n" = "1" ]; then
     timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --cpu-budget 5 > gpurun_out/scale_${TAG}_n1.json 2> gpurun_out/scale_${TAG}_n1.err
   else

@@ -273,7 +273,11 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
 
 __device__ long long g_filter_debug_clock[2];   // {SM cycles, ns} of CTA 0, written in the timing-experiment modes only
 
-template <int kNKB>   // k-blocks of 64 per row: d_pad / 64
+// kNKB: k-blocks of 64 per row (d_pad / 64).  kCluster: 1, or 2 = clusters of two CTAs that work on two different
+// 256-user groups over the SAME item tiles: each CTA fetches half of every tile and TMA-multicasts it into both CTAs'
+// shared memory, so the L2 -> SM stream of the item operand (1 TB per launch at 1M x 1M x d128, the second largest
+// consumer after the MMAs) is halved.
+template <int kNKB, int kCluster>
 __global__ void __launch_bounds__(kFThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -292,7 +296,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   constexpr int n_kb = kNKB;
-  const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * p.n_splits;
+  // work unit = (group of kCluster user pairs, item split); CTA `crank` of the cluster takes pair kCluster * g + crank
+  const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;
+  const int n_groups = (p.n_user_pairs + kCluster - 1) / kCluster;
+  const int64_t n_work = static_cast<int64_t>(n_groups) * p.n_splits;
+  const int64_t w_first = blockIdx.x / kCluster, w_step = gridDim.x / kCluster;
+  constexpr uint16_t kClusterMask = (1u << kCluster) - 1u;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_items);
   if (warp == 1 && lane == 0) {
@@ -303,13 +312,14 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
     }
     for (int i = 0; i < n_slots; ++i) {
       mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
+      mbar_init(b_empty + i, kCluster);   // the MMA warps of all CTAs that received the tile
     }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<kFTmemCols>(tmem_base_smem);
   tcgen05_fence_before();
   __syncthreads();
+  if (kCluster == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   long long dbg_clk = 0, dbg_ns = 0;
@@ -323,8 +333,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
     {   // warp-uniform control flow, one elected lane issues (see the MMA warp)
       int ts = 0;
       uint32_t ts_phase = 0, filled = 0;
-      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = static_cast<int>(w / p.n_user_pairs);
+      for (int64_t w = w_first; w < n_work; w += w_step) {
+        const int sp = static_cast<int>(w / n_groups);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         for (int t = t0; t < t1; ++t) {
@@ -333,9 +343,15 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
           if (elect_one()) {
             mbar_arrive_expect_tx(b_full + ts, kSlotBytes);
 #pragma unroll
-            for (int kb = 0; kb < kNKB; ++kb)
-              tma_load_2d(smem + L.b_off + ts * kSlotBytes + kb * kFBTileBytes, &map_items, b_full + ts, kb * kFKBlock,
-                          t * kFBlockN, kEvictLast);
+            for (int kb = 0; kb < kNKB; ++kb) {
+              if (kCluster == 2)   // this CTA's half of the tile rows (box = 64 rows), delivered to both CTAs
+                tma_load_2d_multicast(smem + L.b_off + ts * kSlotBytes + kb * kFBTileBytes + crank * (kFBTileBytes / 2),
+                                      &map_items, b_full + ts, kb * kFKBlock,
+                                      t * kFBlockN + static_cast<int>(crank) * (kFBlockN / 2), kClusterMask, kEvictLast);
+              else
+                tma_load_2d(smem + L.b_off + ts * kSlotBytes + kb * kFBTileBytes, &map_items, b_full + ts,
+                            kb * kFKBlock, t * kFBlockN, kEvictLast);
+            }
           }
           __syncwarp();
           ++filled;
@@ -366,8 +382,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       int ts = 0;
       uint32_t ts_phase = 0, witer = 0, slot = 0, slot_phase = 0, consumed = 0;
       const uint32_t b_base = smem_u32(smem + L.b_off);
-      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = static_cast<int>(w / p.n_user_pairs);
+      for (int64_t w = w_first; w < n_work; w += w_step) {
+        const int sp = static_cast<int>(w / n_groups);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
@@ -394,7 +410,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
                               db + static_cast<uint64_t>(kb * (kFBTileBytes >> 4) + 2 * ks), idesc,
                               static_cast<uint32_t>(kb > 0 || ks > 0));
               umma_commit(tmem_full + slot);
-              if (b == 1 && streamed) umma_commit(b_empty + ts);
+              if (b == 1 && streamed) {
+                if (kCluster == 2)
+                  umma_commit_multicast(b_empty + ts, kClusterMask);
+                else
+                  umma_commit(b_empty + ts);
+              }
             }
             __syncwarp();
             if (++slot == kFAccSlots) {
@@ -425,9 +446,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t slot = group, slot_use = 0;   // accumulator number q = 2 (tile count) + group: slot q % 3, use q / 3
 
-    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int up = static_cast<int>(w % p.n_user_pairs);
-      const int sp = static_cast<int>(w / p.n_user_pairs);
+    for (int64_t w = w_first; w < n_work; w += w_step) {
+      const int up = static_cast<int>(w % n_groups) * kCluster + static_cast<int>(crank);
+      const int sp = static_cast<int>(w / n_groups);
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
       const int64_t u = (static_cast<int64_t>(up) * 2 + group) * kFBlockM + row;
@@ -536,6 +557,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
 
   tcgen05_fence_before();
   __syncthreads();
+  if (kCluster == 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (p.debug_mode != 0 && blockIdx.x == 0 && threadIdx.x == 64) {
     long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -746,15 +768,53 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
       break;
     }
   TRK_CHECK_ARG(p.n_stages >= 2 * p.n_kblocks, "score_filter: shared memory budget exceeded");
-  rc = make_hi_map(&map_items, item_hi, n_items, d_pad, d_pad, kFBlockN);
-  if (rc != TRK_OK) return rc;
-
   const uint32_t smem_bytes = filter_layout(p.n_stages).total + 1024;
-  auto kernel = p.n_kblocks == 2 ? score_filter_kernel<2> : score_filter_kernel<1>;
-  TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
-  const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
-  kernel<<<grid, kFThreads, smem_bytes, stream>>>(map_items, p);
+
+  // Launch form: clusters of two CTAs sharing every item tile through TMA multicast (default when the device can keep
+  // (almost) all SMs busy with 2-CTA clusters), else independent CTAs.  TRK_FILTER_CLUSTER=1|2 forces one.
+  int cluster = 2;
+  {
+    const char* env = getenv("TRK_FILTER_CLUSTER");
+    if (env != nullptr && (atoi(env) == 1 || atoi(env) == 2)) cluster = atoi(env);
+  }
+  auto kernel2 = p.n_kblocks == 2 ? score_filter_kernel<2, 2> : score_filter_kernel<1, 2>;
+  auto kernel1 = p.n_kblocks == 2 ? score_filter_kernel<2, 1> : score_filter_kernel<1, 1>;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  int max_clusters = 0;
+  if (cluster == 2) {
+    TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(kFThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel2, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      max_clusters = 0;
+    }
+    const char* env = getenv("TRK_FILTER_CLUSTER");
+    if (max_clusters * 2 < sm_count() - 8 && env == nullptr) cluster = 1;   // too many SMs would sit idle
+    if (max_clusters < 1) cluster = 1;
+  }
+  rc = make_hi_map(&map_items, item_hi, n_items, d_pad, d_pad, kFBlockN / cluster);
+  if (rc != TRK_OK) return rc;
+  if (cluster == 2) {
+    const int64_t n_work = ceil_div(static_cast<int64_t>(p.n_user_pairs), 2) * n_splits;
+    const int n_clusters = static_cast<int>(n_work < max_clusters ? n_work : max_clusters);
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * n_clusters));
+    TRK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel2, map_items, p));
+  } else {
+    TRK_CHECK_CUDA(cudaFuncSetAttribute(kernel1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int64_t n_work = static_cast<int64_t>(p.n_user_pairs) * n_splits;
+    const int grid = static_cast<int>(n_work < sm_count() ? n_work : sm_count());
+    kernel1<<<grid, kFThreads, smem_bytes, stream>>>(map_items, p);
+  }
   TRK_CHECK_LAUNCH();
   if (p.debug_mode != 0) {   // timing experiments only: report the SM clock CTA 0 saw (synchronises)
     long long clk[2] = {0, 0};

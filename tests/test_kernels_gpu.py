@@ -452,10 +452,14 @@ def test_filter_candidates_respect_the_error_bound(K, sort_by_bias):
 
 
 @pytest.mark.parametrize('U,I,d,k,integer', [(700, 9000, 128, 10, False), (300, 1500, 64, 5, True), (257, 513, 100, 12, False),
-                                             (513, 40000, 64, 10, False)])
-def test_filter_user_block_and_kblock_shapes(K, U, I, d, k, integer):
+                                             (513, 40000, 64, 10, False), (1100, 3000, 128, 10, False)])
+@pytest.mark.parametrize('cluster', ['1', '2'])
+def test_filter_user_block_and_kblock_shapes(K, monkeypatch, cluster, U, I, d, k, integer):
     """Ragged user blocks (U not a multiple of 256: rows past the end are zero rows in tensor memory), one and two
-    k-blocks (d_pad 64 / 128), several work units per CTA."""
+    k-blocks (d_pad 64 / 128), several work units per CTA; both launch forms: independent CTAs and clusters of two
+    CTAs sharing the item tiles by TMA multicast (an odd number of 256-user groups leaves one CTA of the last cluster
+    without users)."""
+    monkeypatch.setenv('TRK_FILTER_CLUSTER', cluster)
     uf, itf, wu, wi, bu, bi = make_case(U, I, d, integer, seed=U + I, regime='tag' if integer else 'indicator')
     scores = oracle_scores(uf, itf, wu, wi, bu, bi)
     exp_i, exp_s = oracle.top_k_from_scores(scores, k)
