@@ -9,15 +9,19 @@
 //   * the tile's indptr slice and ALL its (col, val) pairs are staged into shared memory with coalesced loads
 //     (the nonzeros of consecutive rows are contiguous in CSR), so the index stream is read from HBM exactly once
 //     and never through scattered 4-entry requests;
-//   * a group of G lanes owns one row; every lane keeps CH float4 accumulators, so one weight row is fetched with
-//     G x 16-byte loads (512 B fully coalesced at d = 128);  4 gathers are kept in flight per lane, 64 warps per SM;
+//   * a group of G lanes owns one row and every lane keeps CH float4 accumulators (d = 128: G = 8, CH = 4, so a warp
+//     works on four rows at once); kBatch x CH 16-byte gathers are in flight per lane, 32 warps per SM.  The launch
+//     bound (4 resident blocks) matters: without it ptxas budgets 32 registers, sinks every gather next to its FMAs and
+//     the kernel runs one memory latency per nonzero -- it then reacts to neither byte count nor L2 hints
+//     (profiles/probe_r1_k1_hints.txt);
 //   * outputs are written with streaming stores (single use);
-//   (round-1 experiment, profiles/r1_v2_k1_ncu.json: warp-private staging + 8 gathers in flight + L2 evict hints was
-//    SLOWER -- 492 us vs 399 us per 1M rows -- because it became issue-bound at half the occupancy, and the hints did
-//    not raise the 20 % L2 hit rate: the 102 MB of randomly re-referenced tag rows exceed what L2 keeps.)
+//   (measured and not kept: L2 eviction-priority hints -- evict_last for re-referenced rows, evict_first for the
+//    once-read ones -- gain ~1.5 %: the 102 MB of randomly re-referenced tag rows of the indicator regime exceed what
+//    the two-partition L2 keeps next to 2 GB of streaming traffic, their hit rate stays ~37 %.)
 //   * accumulation is fp32 FMA in CSR storage order -> bit-identical from run to run, duplicates are summed;
 //   * the epilogue (row still in registers) optionally L2-normalises, writes fp32 and/or the split-fp16 operand
 //     (hi | lo, per-row power-of-two scale) that the tensor-core score kernel consumes.
+
 #include "common.cuh"
 
 namespace trk {
@@ -25,6 +29,21 @@ namespace trk {
 constexpr int kGatherThreads = 256;
 constexpr int kTileRows = 64;
 constexpr int kNnzCap = 3072;  // staged (col,val) pairs per tile: 24 KB
+
+// Weight-row gathers are issued through `asm volatile` and their results pinned by empty volatile asm statements: with
+// plain __ldg the compiler sinks every load next to its FMAs to save registers (32 registers, one gather in flight per
+// lane: four serialised memory latencies per 4-entry row -- the kernel then ignores both byte count and L2 hints,
+// profiles/probe_r1_k1_hints.txt).  This keeps the loads of a batch together, ahead of the first FMA.
+__device__ __forceinline__ float4 ldg_f4_nc(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ float ldg_f1_nc(const float* ptr) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+  return v;
+}
 
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -129,7 +148,7 @@ __device__ __forceinline__ void row_epilogue(float (&acc)[CH][VEC ? 4 : 1], int 
 }
 
 template <int G, int CH, bool VEC>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 4)
 csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
                          const float* __restrict__ val, const float* __restrict__ weights, int64_t rows, int d,
                          int n_normalize, float* __restrict__ out_f32, __half* __restrict__ out_split, int d_pad,
@@ -172,41 +191,52 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
 #pragma unroll
         for (int w = 0; w < W; ++w) acc[j][w] = 0.0f;
 
-      // batches of four entries: all (up to four) gathers of a batch are issued before the first FMA, also for rows
-      // with fewer than four entries left (a scalar tail would serialise one memory latency per entry); FMAs retire
-      // in storage order
-      for (int p = a; p < b; p += 4) {
-        const int n = min(4, b - p);
-        int c[4];
-        float v[4];
+      // batches of kBatch entries: all gathers of a batch are issued before the first FMA, also for rows with fewer
+      // entries left (a scalar tail would serialise one memory latency per entry); FMAs retire in storage order.
+      // kBatch x CH loads of 16 bytes are in flight per lane.
+      constexpr int kBatch = (CH * W >= 16) ? 2 : 4;
+      for (int p = a; p < b; p += kBatch) {
+        const int n = min(kBatch, b - p);
+        int c[kBatch];
+        float v[kBatch];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kBatch; ++q) {
           const int pq = p + (q < n ? q : 0);
           c[q] = staged ? s_col[pq - p0] : __ldg(col + pq);
           v[q] = staged ? s_val[pq - p0] : __ldg(val + pq);
         }
-        float wv[4][CH][W];
+        float wv[kBatch][CH][W];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kBatch; ++q) {
+          // entries past the end of the row re-read entry 0 (c[q] is clamped above) and are skipped by the FMAs;
+          // chunks past d (padding lanes of the split operand) re-read chunk 0 and are zeroed
           const float* wrow = weights + static_cast<int64_t>(c[q]) * d;
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
             const int e0 = (lane + G * j) * W;
-            if (q < n && e0 < d) {
-              if constexpr (VEC) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + e0));
-                wv[q][j][0] = t.x; wv[q][j][1] = t.y; wv[q][j][2] = t.z; wv[q][j][3] = t.w;
-              } else {
-                wv[q][j][0] = __ldg(wrow + e0);
-              }
+            const bool in_row = e0 < d;
+            if constexpr (VEC) {
+              const float4 t = ldg_f4_nc(wrow + (in_row ? e0 : 0));
+              wv[q][j][0] = in_row ? t.x : 0.0f;
+              wv[q][j][1] = in_row ? t.y : 0.0f;
+              wv[q][j][2] = in_row ? t.z : 0.0f;
+              wv[q][j][3] = in_row ? t.w : 0.0f;
             } else {
-#pragma unroll
-              for (int w = 0; w < W; ++w) wv[q][j][w] = 0.0f;
+              const float t = ldg_f1_nc(wrow + (in_row ? e0 : 0));
+              wv[q][j][0] = in_row ? t : 0.0f;
             }
           }
         }
+        // pin: every loaded value passes through an (empty) volatile asm that is ordered after ALL the loads above,
+        // so no FMA can be scheduled in between two gathers
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < kBatch; ++q)
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+#pragma unroll
+            for (int w = 0; w < W; ++w) asm volatile("" : "+f"(wv[q][j][w]));
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
           if (q < n) {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
@@ -324,10 +354,13 @@ bool pick_shape(int d, int d_pad, bool want_split, bool aligned16, RowShape* s) 
   if (d % 4 == 0 && aligned16) {
     const int units = cover / 4;
     s->vec = true;
+    // narrow groups, several 16-byte chunks per lane: a warp then works on 4 (or 2) rows at once, which amortises the
+    // per-row control instructions and puts kBatch x CH gathers in flight per lane (K1 at 1M rows x d128, 4 entries per
+    // row: 32 lanes x 1 chunk 0.52 ms, 16 x 2 0.44 ms, 8 x 4 0.42 ms; scripts/k1_probe.py)
     if (units <= 8) { s->g = 8; s->ch = 1; }
-    else if (units <= 16) { s->g = 16; s->ch = 1; }
-    else if (units <= 32) { s->g = 32; s->ch = 1; }
-    else if (units <= 64) { s->g = 32; s->ch = 2; }
+    else if (units <= 16) { s->g = 8; s->ch = 2; }
+    else if (units <= 32) { s->g = 8; s->ch = 4; }
+    else if (units <= 64) { s->g = 16; s->ch = 4; }
     else if (units <= 128) { s->g = 32; s->ch = 4; }
     else return false;
     return true;
@@ -350,10 +383,10 @@ int gather_grid(int64_t n_tiles) {
 #define TRK_DISPATCH_ROWSHAPE(S, CALL)                          \
   do {                                                          \
     if ((S).vec) {                                              \
-      if ((S).g == 8) { CALL(8, 1, true); }                     \
-      else if ((S).g == 16) { CALL(16, 1, true); }              \
-      else if ((S).ch == 1) { CALL(32, 1, true); }              \
-      else if ((S).ch == 2) { CALL(32, 2, true); }              \
+      if ((S).g == 8 && (S).ch == 1) { CALL(8, 1, true); }      \
+      else if ((S).g == 8 && (S).ch == 2) { CALL(8, 2, true); } \
+      else if ((S).g == 8) { CALL(8, 4, true); }                \
+      else if ((S).g == 16) { CALL(16, 4, true); }              \
       else { CALL(32, 4, true); }                               \
     } else {                                                    \
       if ((S).ch == 1) { CALL(32, 1, false); }                  \
