@@ -537,7 +537,7 @@ class TensorRec(object):
         device = self._cuda_device()
         user_in = self._single_input(user_features, 'user_features')
         item_in = self._single_input(item_features, 'item_features')
-        return self._predict_device(user_in, item_in, device).cpu().numpy()
+        return kernels.to_host(self._predict_device(user_in, item_in, device))
 
     def predict_rank(self, user_features, item_features, k=None):
         """Ranks for every user x item pair: int32 ndarray [n_users, n_items], 1 = best, ties by lower item index
@@ -553,7 +553,7 @@ class TensorRec(object):
         scores = self._predict_device(user_in, item_in, device)
         if scores.numel() == 0:
             return np.zeros(tuple(scores.shape), dtype=np.int32)
-        return kernels.rank_full(scores).cpu().numpy()
+        return kernels.to_host(kernels.rank_full(scores))
 
     def predict_top_k(self, user_features, item_features, k, item_id_offset=0, gather_group=None, to_host=True):
         """The k best items per user in reference rank order, without materialising the score matrix.
@@ -603,7 +603,7 @@ class TensorRec(object):
             top_s, top_i = kernels.topk_merge(all_s, all_i, k)
         if not to_host:
             return TopK(top_i, top_s)
-        return TopK(top_i.cpu().numpy(), top_s.cpu().numpy())
+        return TopK(*kernels.to_host(top_i, top_s))
 
     def predict_similar_items(self, item_features, item_ids, n_similar):
         """tensorrec/tensorrec.py:666-703: for each id, the n_similar (item_id, score) pairs of highest prediction

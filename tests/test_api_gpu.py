@@ -200,6 +200,12 @@ def test_repeat_and_reload_are_bit_identical(T):
     assert np.array_equal(ranks, new_model.predict_rank(uf, itf))
     again = new_model.predict_rank(uf, itf, k=7)
     assert np.array_equal(top.items, again.items) and np.array_equal(top.scores, again.scores)
+    # results come back in page-locked buffers that are recycled once collected: live results must never alias
+    assert not np.shares_memory(top.items, again.items) and not np.shares_memory(predictions, new_model.predict(uf, itf))
+    snapshot = top.items.copy()
+    for _ in range(3):
+        new_model.predict_rank(uf, itf, k=7)
+    assert np.array_equal(top.items, snapshot)
 
 
 # ---- the plugin surface: a user-defined representation graph (test/test_readme.py:33-68) --------------------------

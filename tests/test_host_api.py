@@ -335,3 +335,37 @@ def test_metrics_accept_full_ranks_and_top_k():
     assert abs(f1_score_at_k(ranks, interactions, k=10) - f1_score_at_k(topk, interactions, k=10)) < 1e-12
     n10 = np.mean(ndcg_at_k(ranks, interactions, k=40))
     assert np.mean(ndcg_at_k(ranks, interactions, k=5)) <= n10 < 1
+
+
+def test_host_result_pool_never_aliases_live_results(monkeypatch):
+    """kernels._HostResults hands out page-locked result buffers; one is reused only after the array returned for it
+    (and every view of it) has been collected."""
+    import gc
+    import weakref
+    from tensorrec_b200 import kernels
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, 'empty', lambda *a, pin_memory=False, **k: real_empty(*a, **k))   # no CUDA here
+    pool = kernels._HostResults()
+
+    def hand_out(shape, dtype):
+        buf = pool._take(shape, dtype)
+        arr = buf.numpy()
+        pool._idle.append((buf, weakref.ref(arr)))
+        return arr
+
+    first = hand_out((4, 3), torch.float32)
+    first[:] = 7
+    second = hand_out((4, 3), torch.float32)
+    assert not np.shares_memory(first, second)
+    view = first[:2]
+    del first
+    gc.collect()
+    third = hand_out((4, 3), torch.float32)
+    assert not np.shares_memory(view, third) and np.all(view == 7)      # a view keeps its buffer out of circulation
+    addr = view.__array_interface__['data'][0]
+    del view
+    gc.collect()
+    fourth = hand_out((4, 3), torch.float32)
+    assert fourth.__array_interface__['data'][0] == addr                 # now it is recycled
+    other = hand_out((4, 3), torch.int32)
+    assert other.dtype == np.int32 and not np.shares_memory(other, fourth)
