@@ -296,11 +296,13 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_before = tensorrec_b200._lib.launch_count
     start.record()
     for _ in range(args.steps):
         out = step(record=True)
     end.record()
     barrier()
+    gpu_launches = tensorrec_b200._lib.launch_count - launches_before   # kernel-launching C-ABI calls, counted
     ms_total = start.elapsed_time(end)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -386,7 +388,7 @@ def run_b200(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_ms_step, 'api': 'TensorRec.predict_rank(user_features, item_features, k) on pinned '
                 'host CSR', 'matches_value_arm': same},
-        'gpu_launches': launches_per_step * args.steps,
+        'gpu_launches': int(gpu_launches),
         'roofline': {'kernel': ('score_filter_kernel (trk_score_filter_f16)' if use_filter
                                 else 'score_tc_kernel<topk> (trk_score_topk_f16x3)'), 'bound': 'tensor',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
@@ -486,6 +488,71 @@ def run_dense(args):
                                    'ms_per_launch': kms}}), flush=True)
 
 
+def run_full_ranks(args):
+    """Secondary measurement: predict_rank() in the reference's full mode -- dense scores, then the exact int32 rank of
+    every (user, item) pair (rank_predictions, tensorrec/recommendation_graphs.py:73-82) -- at a shape whose [U, I]
+    matrices fit HBM.  Bound: HBM (the score matrix is written once, read by the chunk sort, the sorted keys are
+    written and re-read by log2(#chunks) merge passes, the ranks are written once)."""
+    import torch
+    from tensorrec_b200 import kernels
+    kernels.require_cuda()
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    uf, itf, wu, wi, bu, bi = make_problem(args)
+    d_pad = kernels.d_pad_for(args.d)
+    ucsr, icsr = kernels.DeviceCSR.from_scipy(uf, device=dev), kernels.DeviceCSR.from_scipy(itf, device=dev)
+    wu_d, wi_d = torch.from_numpy(wu).to(dev), torch.from_numpy(wi).to(dev)
+    bu_d, bi_d = torch.from_numpy(bu).to(dev), torch.from_numpy(bi).to(dev)
+    out = torch.empty((args.users, args.items), dtype=torch.float32, device=dev)
+    ev = []
+
+    def step():
+        _, us, usc = kernels.gather_reduce(ucsr, wu_d, want_f32=False, split_d_pad=d_pad)
+        _, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=False, split_d_pad=d_pad)
+        ub, ib = kernels.project_biases(ucsr, bu_d), kernels.project_biases(icsr, bi_d)
+        meta = kernels.pack_item_meta(isc, ib, args.items)
+        kernels.score_dense_tc(us, usc, ub, its, meta, args.users, args.items, d_pad, out=out)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ranks = kernels.rank_full(out)
+        b.record()
+        ev.append((a, b))
+        return ranks
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    del ev[:]
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        ranks = step()
+    s1.record()
+    torch.cuda.synchronize()
+    ms = s0.elapsed_time(s1) / args.steps
+    kms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # spot check against the closed form on a few rows: rank = 1 + #greater + #equal with a lower index
+    rows = np.linspace(0, args.users - 1, 4).astype(np.int64)
+    sc, rk = out[rows].cpu().numpy(), ranks[rows].cpu().numpy()
+    for r in range(len(rows)):
+        order = np.lexsort((np.arange(args.items), -sc[r].astype(np.float64)))
+        expect = np.empty(args.items, dtype=np.int64)
+        expect[order] = np.arange(1, args.items + 1)
+        assert np.array_equal(expect, rk[r]), 'rank_full disagrees with the closed form on row %d' % rows[r]
+    peaks = measured_peaks()
+    pairs = args.users * float(args.items)
+    alg_bytes = pairs * (4 + 4)        # scores read once, ranks written once
+    gbs = alg_bytes / (kms * 1e-3) / 1e9
+    print(json.dumps({'metric': 'predict_rank_full_ranks_per_s', 'value': pairs / (ms * 1e-3), 'unit': 'ranks/s',
+                      'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+                      'config': {'workload': 'predict_rank() full int32 ranks, %d users x %d items, d=%d (reference '
+                                             'semantics: every pair ranked)' % (args.users, args.items, args.d)},
+                      'roofline': {'kernel': 'rank_chunk_sort_kernel + rank_merge_pass_kernel (trk_rank_full)',
+                                   'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                   'frac': gbs / peaks['hbm_gbs'], 'ms_per_launch': kms,
+                                   'ranks_per_s_kernel': pairs / (kms * 1e-3)}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -496,12 +563,14 @@ def main():
     ap.add_argument('--items', type=int, default=1000000)
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--k', type=int, default=10)
-    ap.add_argument('--workload', default='topk', choices=['topk', 'dense'])
+    ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     args = ap.parse_args()
     if args.workload == 'dense':
         run_dense(args)
+    elif args.workload == 'ranks':
+        run_full_ranks(args)
     elif args.impl == 'reference':
         run_reference(args)
     else:

@@ -81,8 +81,13 @@ def last_error():
     return load().trk_last_error().decode('utf-8', 'replace')
 
 
+launch_count = 0   # successful kernel-launching ABI calls so far (bench.py reports the delta over its timed region)
+
+
 def check(rc, what):
+    global launch_count
     if rc == TRK_OK:
+        launch_count += 1
         return
     msg = '%s: %s' % (what, last_error())
     if rc == TRK_ERR_ARG:

@@ -5,16 +5,19 @@
 //     rank[u,i] = 1 + #{j : s[u,j] > s[u,i]} + #{j < i : s[u,j] == s[u,i]}                    (int32)
 // Each score becomes the 64-bit key (descending-order bits of the float) << 32 | index; keys of a row are unique,
 // ascending key order IS the reference's order, so no stable sort is needed:
-//   pass 1: every chunk of kChunk keys of a row is bitonic-sorted in shared memory;
-//   pass 2 (rows longer than one chunk): the rank of a key is its position in its own chunk plus, for every other
-//           chunk of the row, the number of keys below it (binary search in the chunk staged to shared memory).
+//   pass 1: every chunk of up to kChunk keys of a row is bitonic-sorted by one block: 256 threads x KPT keys each in
+//           REGISTERS -- exchange distances below KPT are compile-time register swaps, distances inside a warp are
+//           shuffles, only the largest distances (<= 6 of the 78 stages at 4096 keys) go through shared memory;
+//   pass 2 (rows longer than one chunk): sorted runs are merged pairwise (merge path: every block produces one tile
+//           of kChunk outputs from the two input windows it locates by binary search), log2(#chunks) passes that
+//           ping-pong between two workspace buffers; the last pass scatters ranks instead of keys.
 // Integer compares only -> exact and run-to-run deterministic.
 #include "common.cuh"
 
 namespace trk {
 
-constexpr int kChunk = 4096;          // keys per sorted chunk: 32 KB of shared memory
-constexpr int kSortThreads = 1024;
+constexpr int kChunk = 4096;          // keys per sorted chunk
+constexpr int kSortThreads = 256;
 constexpr uint64_t kPadKey = ~0ull;   // sorts behind every real key
 
 __device__ __forceinline__ uint64_t rank_key(float s, uint32_t idx) {
@@ -24,89 +27,176 @@ __device__ __forceinline__ uint64_t rank_key(float s, uint32_t idx) {
   return (static_cast<uint64_t>(~asc) << 32) | idx;                  // descending score, ascending index
 }
 
-// In-place ascending bitonic sort of `n` (power of two, <= kChunk) keys in shared memory by the whole block.
-__device__ __forceinline__ void bitonic_sort_smem(uint64_t* keys, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncthreads();
-      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int hi = lo | j;
-        const uint64_t a = keys[lo], b = keys[hi];
-        const bool ascending = (lo & k) == 0;
-        if ((a > b) == ascending) {
-          keys[lo] = b;
-          keys[hi] = a;
+__device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool ascending) {
+  const bool sw = (a > b) == ascending;
+  const uint64_t lo = sw ? b : a, hi = sw ? a : b;
+  a = lo;
+  b = hi;
+}
+
+// One in-register stage: exchange distance J < KPT (compile time, so every register index is static).
+template <int KPT, int J>
+__device__ __forceinline__ void bitonic_stage_regs(uint64_t (&key)[KPT], int k, int tid) {
+#pragma unroll
+  for (int r = 0; r < KPT; ++r) {
+    if ((r & J) == 0) {
+      const bool ascending = ((tid * KPT + r) & k) == 0;
+      cmp_swap(key[r], key[r | J], ascending);
+    }
+  }
+}
+
+// Ascending bitonic sort of kSortThreads * KPT keys held blocked in registers (element e = tid * KPT + r).
+// The (k, j) stage loops stay ROLLED: the fully unrolled network (78 stages x 16 keys at 4096) is ~30k instructions,
+// overflows the instruction cache and ran 3x slower than the shared-memory version it replaces.  Only the register
+// slot loops are unrolled; the in-register stages dispatch on j to one of log2(KPT) specialised bodies.
+template <int KPT>
+__device__ __forceinline__ void block_bitonic_sort(uint64_t (&key)[KPT], uint64_t* s_keys) {
+  constexpr int N = kSortThreads * KPT;
+  constexpr int kLogN = N == 256 ? 8 : N == 512 ? 9 : N == 1024 ? 10 : N == 2048 ? 11 : 12;
+  static_assert((1 << kLogN) == N, "block_bitonic_sort: unsupported size");
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int lk = 1; lk <= kLogN; ++lk) {
+    const int k = 1 << lk;
+#pragma unroll 1
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
+      if (j < KPT) {
+        // partner inside this thread's registers
+        if (KPT > 1 && j == 1) bitonic_stage_regs<KPT, 1 % (KPT > 1 ? KPT : 2)>(key, k, tid);
+        if (KPT > 2 && j == 2) bitonic_stage_regs<KPT, 2 % (KPT > 2 ? KPT : 3)>(key, k, tid);
+        if (KPT > 4 && j == 4) bitonic_stage_regs<KPT, 4 % (KPT > 4 ? KPT : 5)>(key, k, tid);
+        if (KPT > 8 && j == 8) bitonic_stage_regs<KPT, 8 % (KPT > 8 ? KPT : 9)>(key, k, tid);
+      } else {
+        const int m = j / KPT;                            // partner thread = tid ^ m, same register slot
+        const bool lower = (tid & m) == 0;
+        const bool ascending = ((tid * KPT) & k) == 0;    // k >= 2 KPT here: the bit comes from tid alone
+        const bool keep_min = lower == ascending;
+        if (m < 32) {
+          // partner in another lane of the warp
+#pragma unroll
+          for (int r = 0; r < KPT; ++r) {
+            const uint32_t olo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key[r]), m);
+            const uint32_t ohi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(key[r] >> 32), m);
+            const uint64_t other = (static_cast<uint64_t>(ohi) << 32) | olo;
+            key[r] = keep_min ? (other < key[r] ? other : key[r]) : (other > key[r] ? other : key[r]);
+          }
+        } else {
+          // partner in another warp: through shared memory
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < KPT; ++r) s_keys[tid * KPT + r] = key[r];
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < KPT; ++r) {
+            const uint64_t other = s_keys[(tid ^ m) * KPT + r];
+            key[r] = keep_min ? (other < key[r] ? other : key[r]) : (other > key[r] ? other : key[r]);
+          }
         }
       }
     }
   }
-  __syncthreads();
 }
 
 // grid = (chunks per row, rows).  Single-chunk rows are ranked directly.
+template <int KPT>
 __global__ void __launch_bounds__(kSortThreads)
 rank_chunk_sort_kernel(const float* __restrict__ scores, int32_t* __restrict__ ranks, uint64_t* __restrict__ sorted,
-                       int64_t n_items, int n_chunks, int sort_n) {
-  extern __shared__ uint64_t s_keys[];
+                       int64_t n_items, int n_chunks) {
+  __shared__ uint64_t s_keys[kSortThreads * KPT];
   const int64_t row = blockIdx.y;
   const int chunk = blockIdx.x;
   const int64_t base = static_cast<int64_t>(chunk) * kChunk;
   const float* srow = scores + row * n_items;
-  for (int t = threadIdx.x; t < sort_n; t += blockDim.x) {
-    const int64_t i = base + t;
-    s_keys[t] = i < n_items ? rank_key(__ldg(srow + i), static_cast<uint32_t>(i)) : kPadKey;
+  const int tid = threadIdx.x;
+  uint64_t key[KPT];
+#pragma unroll
+  for (int r = 0; r < KPT; ++r) {
+    const int64_t i = base + tid * KPT + r;
+    key[r] = i < n_items ? rank_key(__ldg(srow + i), static_cast<uint32_t>(i)) : kPadKey;
   }
-  bitonic_sort_smem(s_keys, sort_n);
+  block_bitonic_sort<KPT>(key, s_keys);
   if (n_chunks == 1) {
     int32_t* rrow = ranks + row * n_items;
-    for (int t = threadIdx.x; t < sort_n; t += blockDim.x) {
-      const uint64_t key = s_keys[t];
-      if (key != kPadKey) rrow[static_cast<uint32_t>(key)] = t + 1;
-    }
+#pragma unroll
+    for (int r = 0; r < KPT; ++r)
+      if (key[r] != kPadKey) rrow[static_cast<uint32_t>(key[r])] = tid * KPT + r + 1;
   } else {
-    uint64_t* dst = sorted + (row * n_chunks + chunk) * kChunk;
-    for (int t = threadIdx.x; t < kChunk; t += blockDim.x) dst[t] = s_keys[t];
+    uint64_t* dst = sorted + (row * n_chunks + chunk) * kChunk + tid * KPT;   // multi-chunk rows use KPT = 16
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) dst[r] = key[r];
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-rank_merge_count_kernel(const uint64_t* __restrict__ sorted, int32_t* __restrict__ ranks, int64_t n_items,
-                        int n_chunks) {
-  __shared__ uint64_t s_other[kChunk];
-  const int64_t row = blockIdx.y;
-  const int chunk = blockIdx.x;
-  const uint64_t* row_sorted = sorted + row * n_chunks * kChunk;
-  constexpr int kPer = kChunk / kSortThreads;
-  uint64_t mine[kPer];
-  int count[kPer];
-#pragma unroll
-  for (int q = 0; q < kPer; ++q) {
-    const int pos = threadIdx.x + q * kSortThreads;
-    mine[q] = row_sorted[static_cast<int64_t>(chunk) * kChunk + pos];
-    count[q] = pos;  // keys of the own chunk below this one
+// One merge pass over a row of n_chunks sorted runs of `run` keys (the last run may be shorter): runs 2p and 2p+1
+// merge into one run of 2 * run keys.  Block (tile, row) produces outputs [tile * kChunk, +kChunk) of the row.
+// final_pass: the outputs are in their final order -> write rank = position + 1 at the key's item index.
+constexpr int kMergePer = kChunk / kSortThreads;   // 16 outputs per thread
+
+__device__ __forceinline__ int64_t merge_path(const uint64_t* __restrict__ A, int64_t len_a,
+                                              const uint64_t* __restrict__ B, int64_t len_b, int64_t diag) {
+  int64_t lo = diag > len_b ? diag - len_b : 0, hi = diag < len_a ? diag : len_a;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (A[mid] < B[diag - 1 - mid]) lo = mid + 1; else hi = mid;   // keys are unique
   }
-  for (int other = 0; other < n_chunks; ++other) {
-    if (other == chunk) continue;
-    __syncthreads();
-    for (int t = threadIdx.x; t < kChunk; t += kSortThreads)
-      s_other[t] = row_sorted[static_cast<int64_t>(other) * kChunk + t];
-    __syncthreads();
+  return lo;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+rank_merge_pass_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int32_t* __restrict__ ranks,
+                       int64_t n_items, int n_chunks, int64_t run, int final_pass) {
+  __shared__ uint64_t s_in[kChunk];
+  __shared__ int64_t s_split[2];
+  const int64_t row = blockIdx.y;
+  const int64_t row_len = static_cast<int64_t>(n_chunks) * kChunk;
+  const uint64_t* row_src = src + row * row_len;
+  const int64_t out0 = static_cast<int64_t>(blockIdx.x) * kChunk;   // first output position of this tile in the row
+  const int64_t pair_base = (out0 / (2 * run)) * (2 * run);
+  const int64_t len_a = row_len - pair_base < run ? row_len - pair_base : run;
+  const int64_t rest = row_len - pair_base - len_a;
+  const int64_t len_b = rest < run ? rest : run;
+  const uint64_t* A = row_src + pair_base;
+  const uint64_t* B = A + len_a;
+  const int64_t d0 = out0 - pair_base;
+  const int64_t d1 = d0 + kChunk < len_a + len_b ? d0 + kChunk : len_a + len_b;
+  if (threadIdx.x < 2) s_split[threadIdx.x] = merge_path(A, len_a, B, len_b, threadIdx.x == 0 ? d0 : d1);
+  __syncthreads();
+  const int64_t a0 = s_split[0], a1 = s_split[1];
+  const int64_t b0 = d0 - a0, b1 = d1 - a1;
+  const int na = static_cast<int>(a1 - a0), nb = static_cast<int>(b1 - b0);
+  for (int t = threadIdx.x; t < na; t += kSortThreads) s_in[t] = A[a0 + t];
+  for (int t = threadIdx.x; t < nb; t += kSortThreads) s_in[na + t] = B[b0 + t];
+  __syncthreads();
+  const uint64_t* sa = s_in;
+  const uint64_t* sb = s_in + na;
+  // this thread's window of the tile: outputs [dt, dt + kMergePer)
+  const int n_out = na + nb;
+  const int dt = threadIdx.x * kMergePer < n_out ? threadIdx.x * kMergePer : n_out;
+  int lo = dt > nb ? dt - nb : 0, hi = dt < na ? dt : na;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sa[mid] < sb[dt - 1 - mid]) lo = mid + 1; else hi = mid;
+  }
+  int i = lo, j = dt - lo;
+  int32_t* rrow = ranks + row * n_items;
+  uint64_t* drow = dst + row * row_len + out0;
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      // number of keys in s_other below mine[q] (keys are unique): branch-free lower bound over 4096 = 2^12
-      int lo = 0;
-#pragma unroll
-      for (int step = kChunk >> 1; step > 0; step >>= 1)
-        if (s_other[lo + step - 1] < mine[q]) lo += step;
-      if (s_other[lo] < mine[q]) lo += 1;  // covers the last slot
-      count[q] += lo;
+  for (int r = 0; r < kMergePer; ++r) {
+    const int o = dt + r;
+    if (o < n_out) {
+      const bool take_a = j >= nb || (i < na && sa[i] < sb[j]);
+      const uint64_t key = take_a ? sa[i] : sb[j];
+      i += take_a ? 1 : 0;
+      j += take_a ? 0 : 1;
+      if (final_pass) {
+        if (key != kPadKey) rrow[static_cast<uint32_t>(key)] = static_cast<int32_t>(out0 + o + 1);
+      } else {
+        drow[o] = key;
+      }
     }
   }
-  int32_t* rrow = ranks + row * n_items;
-#pragma unroll
-  for (int q = 0; q < kPer; ++q)
-    if (mine[q] != kPadKey) rrow[static_cast<uint32_t>(mine[q])] = count[q] + 1;
 }
 
 static int next_pow2(int64_t n) {
@@ -118,7 +208,8 @@ static int next_pow2(int64_t n) {
 size_t rank_full_workspace_bytes(int64_t n_users, int64_t n_items) {
   if (n_items <= kChunk || n_users <= 0) return 0;
   const int64_t n_chunks = ceil_div(n_items, kChunk);
-  return static_cast<size_t>(n_users) * static_cast<size_t>(n_chunks) * kChunk * sizeof(uint64_t);
+  // two key buffers: the merge passes ping-pong between them
+  return 2 * static_cast<size_t>(n_users) * static_cast<size_t>(n_chunks) * kChunk * sizeof(uint64_t);
 }
 
 int rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_items, void* workspace,
@@ -133,20 +224,33 @@ int rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_it
   TRK_CHECK_ARG(workspace_bytes >= need && (need == 0 || workspace != nullptr),
                 "rank_full: workspace too small (%zu < %zu)", workspace_bytes, need);
   const int sort_n = n_chunks == 1 ? next_pow2(n_items) : kChunk;
-  const int threads = sort_n / 2 < kSortThreads ? (sort_n / 2 < 32 ? 32 : sort_n / 2) : kSortThreads;
+  const int kpt = sort_n <= kSortThreads ? 1 : sort_n / kSortThreads;   // 1, 2, 4, 8 or 16 keys per thread
+  uint64_t* ws0 = static_cast<uint64_t*>(workspace);
+  uint64_t* ws1 = ws0 ? ws0 + static_cast<size_t>(n_users) * n_chunks * kChunk : nullptr;
   // rows go on grid.y (<= 65535 per launch)
   for (int64_t r0 = 0; r0 < n_users; r0 += 65535) {
     const int64_t nr = n_users - r0 < 65535 ? n_users - r0 : 65535;
     const dim3 grid(static_cast<unsigned>(n_chunks), static_cast<unsigned>(nr));
-    uint64_t* ws = static_cast<uint64_t*>(workspace);
-    rank_chunk_sort_kernel<<<grid, threads, sort_n * sizeof(uint64_t), stream>>>(
-        scores + r0 * n_items, ranks + r0 * n_items, ws ? ws + r0 * n_chunks * kChunk : nullptr, n_items,
-        static_cast<int>(n_chunks), sort_n);
+    const float* sc = scores + r0 * n_items;
+    int32_t* rk = ranks + r0 * n_items;
+    uint64_t* a = ws0 ? ws0 + r0 * n_chunks * kChunk : nullptr;
+    uint64_t* b = ws1 ? ws1 + r0 * n_chunks * kChunk : nullptr;
+    const int nc = static_cast<int>(n_chunks);
+    switch (kpt) {
+      case 1: rank_chunk_sort_kernel<1><<<grid, kSortThreads, 0, stream>>>(sc, rk, a, n_items, nc); break;
+      case 2: rank_chunk_sort_kernel<2><<<grid, kSortThreads, 0, stream>>>(sc, rk, a, n_items, nc); break;
+      case 4: rank_chunk_sort_kernel<4><<<grid, kSortThreads, 0, stream>>>(sc, rk, a, n_items, nc); break;
+      case 8: rank_chunk_sort_kernel<8><<<grid, kSortThreads, 0, stream>>>(sc, rk, a, n_items, nc); break;
+      default: rank_chunk_sort_kernel<16><<<grid, kSortThreads, 0, stream>>>(sc, rk, a, n_items, nc); break;
+    }
     TRK_CHECK_LAUNCH();
-    if (n_chunks > 1) {
-      rank_merge_count_kernel<<<grid, kSortThreads, 0, stream>>>(ws + r0 * n_chunks * kChunk, ranks + r0 * n_items,
-                                                                 n_items, static_cast<int>(n_chunks));
+    for (int64_t run = kChunk; run < n_chunks * kChunk; run *= 2) {
+      const int final_pass = 2 * run >= n_chunks * kChunk ? 1 : 0;
+      rank_merge_pass_kernel<<<grid, kSortThreads, 0, stream>>>(a, b, rk, n_items, nc, run, final_pass);
       TRK_CHECK_LAUNCH();
+      uint64_t* t = a;
+      a = b;
+      b = t;
     }
   }
   return TRK_OK;

@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.trk_version() == 1000
     assert lib.trk_score_topk_max_k(128) >= 10 and lib.trk_score_topk_max_k(96) == 0
     assert lib.trk_rank_full_workspace_bytes(10, 100) == 0
-    assert lib.trk_rank_full_workspace_bytes(3, 5000) == 3 * 2 * 4096 * 8
+    assert lib.trk_rank_full_workspace_bytes(3, 5000) == 2 * 3 * 2 * 4096 * 8     # two ping-pong key buffers
 
 
 def test_argument_errors_are_reported_through_the_abi():

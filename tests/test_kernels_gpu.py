@@ -196,7 +196,8 @@ def test_rank_full_golden(K):
     assert got.dtype == np.int32 and np.array_equal(got, np.array(g['expected']))
 
 
-@pytest.mark.parametrize('U,I', [(3, 1), (7, 2), (100, 150), (33, 1000), (5, 4096), (9, 4097), (6, 9000), (3, 20000)])
+@pytest.mark.parametrize('U,I', [(3, 1), (7, 2), (100, 150), (40, 256), (40, 257), (33, 1000), (17, 2048), (5, 4096), (9, 4097),
+                                 (6, 9000), (4, 12293), (3, 20000), (2, 70001)])
 def test_rank_full_matches_double_sort_with_ties(K, U, I):
     rng = np.random.default_rng(I)
     s = rng.integers(-4, 5, size=(U, I)).astype(F32)           # heavy ties
