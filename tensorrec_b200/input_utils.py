@@ -71,6 +71,14 @@ class SparseInput(object):
             self._csr[key] = DeviceCSR.from_scipy(self.matrix, device=device)
         return self._csr[key]
 
+    def device_csr_t(self, device):
+        """CSR of the transposed matrix on the device (the backward operand of the K1 training step)."""
+        from .kernels import DeviceCSR
+        key = 'T:' + str(device)
+        if key not in self._csr:
+            self._csr[key] = DeviceCSR.from_scipy_transposed(self.matrix, device=device)
+        return self._csr[key]
+
     def torch_sparse(self, device):
         """Uncoalesced COO tensor in reference entry order (duplicates are summed by torch.sparse.mm)."""
         key = str(device)
@@ -79,4 +87,6 @@ class SparseInput(object):
             idx = torch.from_numpy(np.stack([ds.row_index, ds.col_index]))
             self._torch[key] = torch.sparse_coo_tensor(idx, torch.from_numpy(ds.values), size=self.shape,
                                                        is_coalesced=False, check_invariants=False).to(device)
+            # lets sparse_ops.sparse_dense_matmul find the CSR forms of this matrix (K1 forward / backward)
+            self._torch[key]._trk_source = self
         return self._torch[key]

@@ -73,6 +73,27 @@ class DeviceCSR(object):
         return (indptr.astype(np.int32), np.ascontiguousarray(coo.col[order], dtype=np.int32),
                 np.ascontiguousarray(coo.data[order], dtype=np.float32))
 
+    @staticmethod
+    def host_arrays_transposed(matrix):
+        """CSR arrays of the TRANSPOSE (one row per feature column), entries of a column in ascending row order and,
+        within a row, in reference entry order; duplicates are kept.  K1 on these arrays is the backward of K1:
+        dW = A^T . dRepr (tf.sparse_tensor_dense_matmul's gradient w.r.t. the dense operand)."""
+        indptr, col, val = DeviceCSR.host_arrays(matrix)
+        n_rows, n_cols = matrix.shape
+        rows = np.repeat(np.arange(n_rows, dtype=np.int32), np.diff(indptr))
+        order = np.argsort(col, kind='stable')
+        counts = np.bincount(col, minlength=n_cols)
+        indptr_t = np.zeros(n_cols + 1, dtype=np.int64)
+        np.cumsum(counts, out=indptr_t[1:])
+        return indptr_t.astype(np.int32), np.ascontiguousarray(rows[order]), np.ascontiguousarray(val[order])
+
+    @classmethod
+    def from_scipy_transposed(cls, matrix, device='cuda'):
+        require_cuda()
+        indptr, col, val = cls.host_arrays_transposed(matrix)
+        up = lambda a: torch.from_numpy(a).to(device, non_blocking=True)   # noqa: E731
+        return cls(up(indptr), up(col), up(val), (matrix.shape[1], matrix.shape[0]))
+
     @classmethod
     def from_scipy(cls, matrix, device='cuda', pin=False):
         require_cuda()

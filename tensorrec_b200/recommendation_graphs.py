@@ -40,7 +40,8 @@ def project_biases(tf_features, n_features):
     if isinstance(tf_features, torch.Tensor):
         tf_feature_biases = get_variable('feature_biases_{}x{}'.format(tf_features.shape[0], n_features),
                                          lambda: torch.zeros([n_features, 1], device=tf_features.device))
-        projected = torch.sum(torch.sparse.mm(tf_features, tf_feature_biases), dim=1)
+        from .sparse_ops import sparse_dense_matmul
+        projected = torch.sum(sparse_dense_matmul(tf_features, tf_feature_biases), dim=1)
         return tf_feature_biases, projected
     if sp.issparse(tf_features):
         tf_features = kernels.DeviceCSR.from_scipy(tf_features)

@@ -24,8 +24,10 @@ def _random_normal(shape, stddev, like):
 
 
 def _sparse_dense_matmul(tf_features, weights):
-    """tf.sparse_tensor_dense_matmul (differentiable w.r.t. the dense operand)."""
-    return torch.sparse.mm(tf_features, weights)
+    """tf.sparse_tensor_dense_matmul (differentiable w.r.t. the dense operand): K1 forward, K1 on the transposed CSR
+    backward when the features live on the CUDA device (sparse_ops.py)."""
+    from .sparse_ops import sparse_dense_matmul
+    return sparse_dense_matmul(tf_features, weights)
 
 
 class AbstractRepresentationGraph(object):

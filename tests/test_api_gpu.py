@@ -302,3 +302,35 @@ def test_recommendation_graph_functions_evaluate_on_the_device(T):
     got = RG.predict_similar_items(PG.CosineSimilarityPredictionGraph(), np.array(g['item_repr'], dtype=F32),
                                    g['item_ids'])
     assert np.array_equal(got.cpu().numpy(), np.array(g['expected'], dtype=F32))
+
+
+# ---- the training step runs the representation through K1 (forward) and K1 on A^T (backward) ---------
+def test_training_matmul_runs_on_k1_and_matches_torch_sparse(T):
+    import torch
+    from tensorrec_b200.input_utils import SparseInput
+    from tensorrec_b200.sparse_ops import sparse_dense_matmul
+    rng = np.random.default_rng(5)
+    for rows, feats, d in ((300, 120, 16), (257, 90, 7), (40, 33, 1)):
+        nnz = rows * 6
+        r, c = rng.integers(0, rows, nnz), rng.integers(0, feats, nnz)          # duplicates on purpose
+        a = sp.coo_matrix((rng.standard_normal(nnz).astype(np.float32), (r, c)), shape=(rows, feats))
+        src = SparseInput(a)
+        tf_a = src.torch_sparse(torch.device('cuda'))
+        w1 = torch.randn(feats, d, device='cuda', requires_grad=True)
+        w2 = w1.detach().clone().requires_grad_(True)
+        g = torch.randn(rows, d, device='cuda')
+        out1 = sparse_dense_matmul(tf_a, w1)
+        out2 = torch.sparse.mm(tf_a, w2)
+        assert type(out1.grad_fn).__name__.startswith('_CsrMatmul')
+        (out1 * g).sum().backward()
+        (out2 * g).sum().backward()
+        scale = float(out2.abs().max()) + 1e-6
+        assert float((out1 - out2).abs().max()) <= 1e-5 * scale
+        assert float((w1.grad - w2.grad).abs().max()) <= 1e-5 * (float(w2.grad.abs().max()) + 1e-6)
+        again = sparse_dense_matmul(tf_a, w1.detach().clone().requires_grad_(True))
+        assert torch.equal(again, out1)                                           # deterministic forward
+    # and fit() of the built-in linear graphs goes through it (loss decreases, results finite)
+    interactions, uf, itf = T.util.generate_dummy_data(num_users=60, num_items=80, interaction_density=.2, seed=2)
+    model = T.TensorRec(n_components=8)
+    model.fit(interactions, uf, itf, epochs=30, learning_rate=.05)
+    assert np.all(np.isfinite(model.predict(uf, itf)))

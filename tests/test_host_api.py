@@ -369,3 +369,22 @@ def test_host_result_pool_never_aliases_live_results(monkeypatch):
     assert fourth.__array_interface__['data'][0] == addr                 # now it is recycled
     other = hand_out((4, 3), torch.int32)
     assert other.dtype == np.int32 and not np.shares_memory(other, fourth)
+
+
+def test_transposed_csr_keeps_duplicates_and_row_order():
+    """DeviceCSR.host_arrays_transposed: the backward operand of the K1 training step (dW = A^T . d_out)."""
+    rows = np.array([2, 0, 2, 1, 2, 0], dtype=np.int64)
+    cols = np.array([1, 3, 1, 0, 3, 3], dtype=np.int64)          # (2, 1) twice; unsorted COO
+    vals = np.array([1.5, -2.0, 0.25, 4.0, 3.0, 7.0], dtype=np.float32)
+    a = sp.coo_matrix((vals, (rows, cols)), shape=(3, 5))
+    indptr, col, val = DeviceCSR.host_arrays_transposed(a)
+    assert indptr.dtype == np.int32 and col.dtype == np.int32 and val.dtype == np.float32
+    assert list(indptr) == [0, 1, 3, 3, 6, 6]                     # columns 2 and 4 are empty
+    assert list(col) == [1, 2, 2, 0, 0, 2]                        # ascending row inside a column, duplicates kept
+    assert list(val) == [4.0, 1.5, 0.25, -2.0, 7.0, 3.0]          # (2,1): storage order 1.5 then 0.25
+    g = np.arange(12, dtype=np.float64).reshape(3, 4)
+    dense_t = np.zeros((5, 3))
+    for f in range(5):
+        for p in range(indptr[f], indptr[f + 1]):
+            dense_t[f, col[p]] += val[p]
+    assert np.allclose(dense_t @ g, a.toarray().T.astype(np.float64) @ g)
