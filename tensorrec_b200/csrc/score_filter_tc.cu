@@ -104,16 +104,6 @@ __host__ __device__ inline FilterLayout filter_layout(int n_stages) {
 // shared-memory ring fed by one bulk copy per tile put the copy's ~2 us latency on the critical path of every
 // second tile: TRK_FILTER_DEBUG=6 showed 112 cycles per MMA step against 64 for the bare instruction stream.)
 
-__device__ __forceinline__ float4 f_lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float f_lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void f_sts64(uint32_t addr, float s, int32_t id) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(s)), "r"(id) : "memory");
 }
