@@ -784,9 +784,23 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel2, &cfg) != cudaSuccess) {
-      (void)cudaGetLastError();
-      max_clusters = 0;
+    // the answer depends on (device, kernel, shared memory) only: asked once per device and kernel variant
+    static int cached_clusters[64][2];
+    static bool cached_valid[64][2];
+    int device = 0;
+    TRK_CHECK_CUDA(cudaGetDevice(&device));
+    const int variant = p.n_kblocks == 2 ? 1 : 0;
+    if (device >= 0 && device < 64 && cached_valid[device][variant]) {
+      max_clusters = cached_clusters[device][variant];
+    } else {
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel2, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        max_clusters = 0;
+      }
+      if (device >= 0 && device < 64) {
+        cached_clusters[device][variant] = max_clusters;
+        cached_valid[device][variant] = true;
+      }
     }
     const char* env = getenv("TRK_FILTER_CLUSTER");
     if (max_clusters * 2 < sm_count() - 8 && env == nullptr) cluster = 1;   // too many SMs would sit idle
