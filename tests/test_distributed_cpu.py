@@ -70,3 +70,10 @@ def test_all_gather_candidates_world_size_2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(str(tmp_path))) == ['ok_0', 'ok_1']
+
+
+def test_all_gather_candidates_world_size_3_uneven_shards(tmp_path):
+    """101 items over 3 ranks: shards of 34 / 34 / 33 items, cross-shard ties resolve to the lower global id."""
+    world = 3
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(str(tmp_path))) == ['ok_0', 'ok_1', 'ok_2']

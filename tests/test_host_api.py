@@ -388,3 +388,15 @@ def test_transposed_csr_keeps_duplicates_and_row_order():
         for p in range(indptr[f], indptr[f + 1]):
             dense_t[f, col[p]] += val[p]
     assert np.allclose(dense_t @ g, a.toarray().T.astype(np.float64) @ g)
+
+
+def test_bias_processing_order_is_a_stable_descending_sort():
+    """kernels.bias_processing_order: the item order the filter kernel sweeps (highest bias first, ties by lower
+    item index -> the order, and with it every result, is deterministic)."""
+    from tensorrec_b200 import kernels
+    rng = np.random.default_rng(11)
+    bias = rng.integers(-3, 4, size=5000).astype(np.float32) * 0.25          # many exact ties
+    perm = kernels.bias_processing_order(torch.from_numpy(bias))
+    assert perm.dtype == torch.int32
+    assert np.array_equal(perm.numpy(), np.argsort(-bias, kind='stable'))
+    assert kernels.bias_processing_order(None) is None
