@@ -9,7 +9,9 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 Parity pinning status (see DESIGN.md "Oracle"):
   * pinned by the reference's own known-answer tests (ported as data in tests/golden/):
     dot / cosine dense prediction, project_biases, bias_prediction_dense, rank_predictions,
-    collapse_mixture_of_tastes (max and attention softmax), predict_similar_items.
+    collapse_mixture_of_tastes (max and attention softmax), predict_similar_items; and, for the training
+    step, the serial dot / cosine / euclidean predictions, bias_prediction_serial,
+    densify_sampled_item_predictions, split_sparse_tensor_indices.
   * PARITY UNPINNED (no reference test holds a number, and TensorFlow -- the reference's only
     numeric back-end -- is not installable here, so the reference cannot be run):
     LinearRepresentationGraph / NormalizedLinearRepresentationGraph values for d > 1,
@@ -25,6 +27,12 @@ from .reference_ops import (  # noqa: F401
     dot_product_dense,
     cosine_dense,
     euclidean_dense,
+    dot_product_serial,
+    cosine_serial,
+    euclidean_serial,
+    split_sparse_tensor_indices,
+    bias_prediction_serial,
+    densify_sampled_item_predictions,
     collapse_mixture_of_tastes,
     project_biases,
     bias_prediction_dense,

@@ -97,6 +97,50 @@ def euclidean_dense(user_repr, item_repr, epsilon=1e-16):
 
 
 # ---------------------------------------------------------------------------------------------------
+# f1 (training step): the serial forms -- one prediction per (user, item) index pair
+# ---------------------------------------------------------------------------------------------------
+def dot_product_serial(user_repr, item_repr, x_user, x_item):
+    """DotProductPredictionGraph.connect_serial_prediction_graph (prediction_graphs.py:52-55): gather both rows,
+    multiply elementwise, reduce_sum over the components."""
+    u = np.asarray(user_repr, dtype=F32)[np.asarray(x_user)]
+    i = np.asarray(item_repr, dtype=F32)[np.asarray(x_item)]
+    return np.sum(u * i, axis=1, dtype=F32)
+
+
+def cosine_serial(user_repr, item_repr, x_user, x_item):
+    """CosineSimilarityPredictionGraph serial (prediction_graphs.py:67-72): l2_normalize rows, then the dot form."""
+    return dot_product_serial(l2_normalize(user_repr), l2_normalize(item_repr), x_user, x_item)
+
+
+def euclidean_serial(user_repr, item_repr, x_user, x_item, epsilon=1e-16):
+    """EuclideanSimilarityPredictionGraph serial (prediction_graphs.py:102-117): -sqrt(max(sum((u - i)^2), eps))."""
+    u = np.asarray(user_repr, dtype=F32)[np.asarray(x_user)]
+    i = np.asarray(item_repr, dtype=F32)[np.asarray(x_item)]
+    distance = np.maximum(np.sum((u - i) ** 2, axis=1, dtype=F32), F32(epsilon))
+    return (F32(-1.0) * np.sqrt(distance)).astype(F32)
+
+
+def split_sparse_tensor_indices(matrix):
+    """split_sparse_tensor_indices (recommendation_graphs.py:22-30) of the SparseTensor built from a scipy matrix
+    (tensorrec.py:285-293): the row and the column index of every stored entry, in COO order."""
+    row, col = coo_from_sparse(matrix)[:2]
+    return row, col
+
+
+def bias_prediction_serial(prediction_serial, projected_user_biases, projected_item_biases, x_user, x_item):
+    """pred + gather(ub, x_user) + gather(ib, x_item), left to right (recommendation_graphs.py:44-57)."""
+    p = np.asarray(prediction_serial, dtype=F32)
+    ub = np.asarray(projected_user_biases, dtype=F32)[np.asarray(x_user)]
+    ib = np.asarray(projected_item_biases, dtype=F32)[np.asarray(x_item)]
+    return ((p + ub).astype(F32) + ib).astype(F32)
+
+
+def densify_sampled_item_predictions(sample_predictions_serial, n_sampled_items, n_users):
+    """reshape to [n_users, n_sampled_items] (recommendation_graphs.py:60-70)."""
+    return np.asarray(sample_predictions_serial).reshape(int(n_users), int(n_sampled_items))
+
+
+# ---------------------------------------------------------------------------------------------------
 # a6: taste collapse -- tensorrec/recommendation_graphs.py:85-109
 # ---------------------------------------------------------------------------------------------------
 def collapse_mixture_of_tastes(tastes_predictions, tastes_attentions=None):

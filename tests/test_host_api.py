@@ -400,3 +400,41 @@ def test_bias_processing_order_is_a_stable_descending_sort():
     assert perm.dtype == torch.int32
     assert np.array_equal(perm.numpy(), np.argsort(-bias, kind='stable'))
     assert kernels.bias_processing_order(None) is None
+
+
+# ---- the host mirror's serial forms against the reference's known answers ---------------------------
+def test_serial_prediction_graphs_match_the_reference_known_answers():
+    import json
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_known_answers.json')))
+    from tensorrec_b200.recommendation_graphs import (
+        bias_prediction_serial, densify_sampled_item_predictions, split_sparse_tensor_indices)
+
+    def t(x, dtype=torch.float32):
+        return torch.tensor(x, dtype=dtype)
+
+    for key, graph in (('dot_product_serial', DotProductPredictionGraph()),
+                       ('cosine_serial', CosineSimilarityPredictionGraph()),
+                       ('euclidean_serial', EuclideanSimilarityPredictionGraph())):
+        g = golden[key]
+        got = graph.connect_serial_prediction_graph(
+            tf_user_representation=t(g['user_repr']), tf_item_representation=t(g['item_repr']),
+            tf_x_user=t(g['x_user'], torch.long), tf_x_item=t(g['x_item'], torch.long)).numpy()
+        expect = np.array(g['expected']) if 'expected' in g else -np.sqrt(np.array(g['expected_neg_sqrt_of']))
+        assert np.allclose(got, expect, atol=1e-6), key
+
+    g = golden['split_sparse_tensor_indices']
+    interactions = SparseInput(sp.coo_matrix(np.array(g['interactions'], dtype=np.float32)))
+    x_user, x_item = split_sparse_tensor_indices(tf_sparse_tensor=interactions.torch_sparse('cpu'), n_dimensions=2)
+    assert x_user.tolist() == g['expected_user'] and x_item.tolist() == g['expected_item']
+
+    g = golden['bias_prediction_serial']
+    got = bias_prediction_serial(
+        tf_prediction_serial=t(g['predictions']), tf_projected_user_biases=t(g['user_biases']),
+        tf_projected_item_biases=t(g['item_biases']), tf_x_user=t(g['x_user'], torch.long),
+        tf_x_item=t(g['x_item'], torch.long)).numpy()
+    assert np.array_equal(got, np.array(g['expected'], dtype=np.float32))
+
+    g = golden['densify_sampled_item_predictions']
+    got = densify_sampled_item_predictions(tf_sample_predictions_serial=t(g['input'], torch.long),
+                                           tf_n_sampled_items=g['n_sampled_items'], tf_n_users=g['n_users']).numpy()
+    assert np.array_equal(got, np.array(g['expected']))

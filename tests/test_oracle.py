@@ -140,3 +140,39 @@ def test_oracle_model_composition_order():
                                           oracle.project_biases(icoo, bi))
     assert np.array_equal(pred, expect)
     assert np.array_equal(m.predict_rank(uf, itf), oracle.rank_predictions(pred))
+
+
+# ---- the serial forms used by the training step -------------------------------------------------------
+def test_serial_predictions_golden():
+    g = GOLDEN['dot_product_serial']
+    got = oracle.dot_product_serial(arr(g['user_repr']), arr(g['item_repr']), g['x_user'], g['x_item'])
+    assert got.dtype == F32 and np.allclose(got, arr(g['expected']))
+    g = GOLDEN['cosine_serial']
+    got = oracle.cosine_serial(arr(g['user_repr']), arr(g['item_repr']), g['x_user'], g['x_item'])
+    assert np.allclose(got, arr(g['expected']), atol=1e-6)
+    g = GOLDEN['euclidean_serial']
+    got = oracle.euclidean_serial(arr(g['user_repr']), arr(g['item_repr']), g['x_user'], g['x_item'])
+    expect = -np.sqrt(np.array(g['expected_neg_sqrt_of']))
+    assert np.allclose(got, expect, atol=1e-6)
+
+
+def test_serial_forms_equal_the_dense_forms_entry_by_entry():
+    rng = np.random.default_rng(4)
+    u, i = rng.standard_normal((7, 5)).astype(F32), rng.standard_normal((9, 5)).astype(F32)
+    xu, xi = np.repeat(np.arange(7), 9), np.tile(np.arange(9), 7)
+    assert np.allclose(oracle.dot_product_serial(u, i, xu, xi).reshape(7, 9), oracle.dot_product_dense(u, i), atol=1e-5)
+    assert np.allclose(oracle.cosine_serial(u, i, xu, xi).reshape(7, 9), oracle.cosine_dense(u, i), atol=1e-5)
+    assert np.allclose(oracle.euclidean_serial(u, i, xu, xi).reshape(7, 9), oracle.euclidean_dense(u, i), atol=1e-4)
+
+
+def test_split_indices_bias_serial_and_densify_golden():
+    g = GOLDEN['split_sparse_tensor_indices']
+    x_user, x_item = oracle.split_sparse_tensor_indices(sp.coo_matrix(arr(g['interactions'])))
+    assert np.array_equal(x_user, g['expected_user']) and np.array_equal(x_item, g['expected_item'])
+    g = GOLDEN['bias_prediction_serial']
+    got = oracle.bias_prediction_serial(arr(g['predictions']), arr(g['user_biases']), arr(g['item_biases']),
+                                        g['x_user'], g['x_item'])
+    assert np.array_equal(got, arr(g['expected']))
+    g = GOLDEN['densify_sampled_item_predictions']
+    got = oracle.densify_sampled_item_predictions(np.array(g['input']), g['n_sampled_items'], g['n_users'])
+    assert np.array_equal(got, np.array(g['expected']))
