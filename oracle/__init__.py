@@ -44,3 +44,4 @@ from .reference_ops import (  # noqa: F401
     predict_similar_items,
     OracleModel,
 )
+from . import loss_ops  # noqa: F401,E402  (training-step losses; parity unpinned)

@@ -438,3 +438,34 @@ def test_serial_prediction_graphs_match_the_reference_known_answers():
     got = densify_sampled_item_predictions(tf_sample_predictions_serial=t(g['input'], torch.long),
                                            tf_n_sampled_items=g['n_sampled_items'], tf_n_users=g['n_users']).numpy()
     assert np.array_equal(got, np.array(g['expected']))
+
+
+def test_loss_graphs_match_the_oracle_restatement():
+    """Host mirror (torch) vs oracle/loss_ops.py (numpy, follows tensorrec/loss_graphs.py line by line) on random
+    inputs with duplicates, non-positive interactions and empty rows."""
+    from oracle import loss_ops as L
+    rng = np.random.default_rng(21)
+    n_users, n_items, n_sampled = 13, 17, 5
+    nnz = 60
+    row, col = rng.integers(0, n_users, nnz), rng.integers(0, n_items, nnz)
+    val = rng.integers(-1, 4, nnz).astype(np.float32)
+    inter = sp.coo_matrix((val, (row, col)), shape=(n_users, n_items))
+    coo = oracle.coo_from_sparse(inter)
+    tf_inter = SparseInput(inter).torch_sparse('cpu')
+    pred = rng.standard_normal((n_users, n_items)).astype(np.float32)
+    pred_serial = pred[coo[0], coo[1]]
+    samples = rng.standard_normal((n_users, n_sampled)).astype(np.float32)
+    t = torch.from_numpy
+    kw = dict(tf_prediction_serial=t(pred_serial), tf_interactions_serial=t(coo[2]), tf_interactions=tf_inter,
+              tf_n_users=n_users, tf_n_items=n_items, tf_prediction=t(pred), tf_rankings=None,
+              tf_sample_predictions=t(samples), tf_n_sampled_items=n_sampled)
+    pairs = [(RMSELossGraph(), L.rmse(pred_serial, coo[2])),
+             (RMSEDenseLossGraph(), L.rmse_dense(coo, pred)),
+             (SeparationLossGraph(), L.separation(pred_serial, coo[2])),
+             (SeparationDenseLossGraph(), L.separation_dense(pred, coo)),
+             (WMRBLossGraph(), L.wmrb(pred_serial, coo, samples, n_items, n_sampled)),
+             (BalancedWMRBLossGraph(), L.balanced_wmrb(pred_serial, coo, samples, n_items, n_sampled))]
+    for graph, expect in pairs:
+        got = graph.connect_loss_graph(**kw).numpy()
+        assert got.shape == np.shape(expect), type(graph).__name__
+        assert np.allclose(got, expect, rtol=2e-5, atol=2e-6), type(graph).__name__

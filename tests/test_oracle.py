@@ -176,3 +176,25 @@ def test_split_indices_bias_serial_and_densify_golden():
     g = GOLDEN['densify_sampled_item_predictions']
     got = oracle.densify_sampled_item_predictions(np.array(g['input']), g['n_sampled_items'], g['n_users'])
     assert np.array_equal(got, np.array(g['expected']))
+
+
+# ---- loss graphs (parity unpinned by the reference: hand-computed cases) ------------------------------
+def test_loss_oracle_hand_computed_cases():
+    from oracle import loss_ops as L
+    assert abs(float(L.rmse([1.0, 2.0, 4.0], [1.0, 0.0, 0.0])) - math.sqrt((0 + 4 + 16) / 3.0)) < 1e-6
+    inter = oracle.coo_from_sparse(sp.coo_matrix(np.array([[1.0, 0.0], [0.0, 2.0]], dtype=F32)))
+    pred = np.array([[0.5, 0.5], [1.0, 1.0]], dtype=F32)
+    assert abs(float(L.rmse_dense(inter, pred)) - math.sqrt((0.25 + 0.25 + 1.0 + 1.0) / 4.0)) < 1e-6
+    # one positive interaction (user 1, item 0, prediction 0.5), two sampled items with predictions 0.0 and 2.0:
+    # margins max(0, 1 - 0.5 + 0) = 0.5 and max(0, 1 - 0.5 + 2) = 2.5 -> log(1 + 10 / 2 * 3.0)
+    inter = oracle.coo_from_sparse(sp.coo_matrix(np.array([[0.0, -1.0], [3.0, 0.0]], dtype=F32)))
+    pred_serial = np.array([9.0, 0.5], dtype=F32)                       # COO order: (0,1) = -1 first, then (1,0) = 3
+    samples = np.array([[7.0, 7.0], [0.0, 2.0]], dtype=F32)
+    got = L.wmrb(pred_serial, inter, samples, n_items=10, n_sampled_items=2)
+    assert got.shape == (1,) and abs(float(got[0]) - math.log(1.0 + 5.0 * 3.0)) < 1e-6
+    # balanced: x interaction value 3 / item 0's positive mass 3 -> unchanged here
+    got_b = L.balanced_wmrb(pred_serial, inter, samples, n_items=10, n_sampled_items=2)
+    assert abs(float(got_b[0]) - float(got[0])) < 1e-6
+    # separation: positives {2, 4} (mean 3, var 1), negatives {0, 0} (mean 0, var 0): 1 - Phi((0 - (-3)) / 1)
+    sep = L.separation([2.0, 4.0, 0.0, 0.0], [1.0, 5.0, 0.0, -2.0])
+    assert abs(float(sep) - (1.0 - 0.5 * (1.0 + math.erf(3.0 / math.sqrt(2.0))))) < 1e-6
