@@ -26,99 +26,100 @@ def _ranks_of_positives(predicted_ranks, positive):
     return sp.csr_matrix(np.asarray(predicted_ranks) * positive.toarray())
 
 
+def _hits_within_k(predicted_ranks, test_interactions, k):
+    """(positives per user, positives ranked <= k per user): the two counts precision and recall are made of."""
+    positives = sp.csr_matrix(sp.csr_matrix(test_interactions) > 0)
+    ranks = _ranks_of_positives(predicted_ranks, positives)
+    n_positive = np.asarray(positives.getnnz(axis=1)).reshape(-1)
+    inside = sp.csr_matrix((ranks.data <= k, ranks.indices, ranks.indptr), shape=ranks.shape)
+    n_hit = np.asarray(inside.sum(axis=1)).reshape(-1)
+    return n_positive, n_hit
+
+
 def precision_at_k(predicted_ranks, test_interactions, k=10, preserve_rows=False):
-    """eval.py:7-30."""
-    positive_test_interactions = sp.csr_matrix(test_interactions > 0)
-    ranks = _ranks_of_positives(predicted_ranks, positive_test_interactions)
-    ranks.data = np.less(ranks.data, (k + 1)).astype(ranks.data.dtype)
-    precision = np.squeeze(np.array(ranks.sum(axis=1))).astype(float) / k
-    if not preserve_rows:
-        precision = precision[positive_test_interactions.getnnz(axis=1) > 0]
-    return precision
+    """Share of the k recommended items that are positives (eval.py:7-30).  preserve_rows keeps users without test
+    interactions (value 0)."""
+    n_positive, n_hit = _hits_within_k(predicted_ranks, test_interactions, k)
+    precision = n_hit.astype(float) / k
+    return precision if preserve_rows else precision[n_positive > 0]
 
 
 def recall_at_k(predicted_ranks, test_interactions, k=10, preserve_rows=False):
-    """eval.py:33-58."""
-    positive_test_interactions = sp.csr_matrix(test_interactions > 0)
-    ranks = _ranks_of_positives(predicted_ranks, positive_test_interactions)
-    ranks.data = np.less(ranks.data, (k + 1)).astype(ranks.data.dtype)
-    retrieved = np.squeeze(positive_test_interactions.getnnz(axis=1))
-    hit = np.squeeze(np.array(ranks.sum(axis=1)))
+    """Share of a user's positives found in the first k ranks (eval.py:33-58; users without positives: 0/0 = nan when
+    preserve_rows, dropped otherwise)."""
+    n_positive, n_hit = _hits_within_k(predicted_ranks, test_interactions, k)
     if not preserve_rows:
-        hit = hit[positive_test_interactions.getnnz(axis=1) > 0]
-        retrieved = retrieved[positive_test_interactions.getnnz(axis=1) > 0]
-    return hit.astype(float) / retrieved.astype(float)
+        keep = n_positive > 0
+        n_positive, n_hit = n_positive[keep], n_hit[keep]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return n_hit.astype(float) / n_positive.astype(float)
 
 
 def _setup_ndcg(predicted_ranks, test_interactions, k=10):
-    """eval.py:61-72."""
-    test_interactions = sp.csr_matrix(test_interactions)
-    pos_inter = sp.csr_matrix(test_interactions > 0)
-    ror = _ranks_of_positives(predicted_ranks, pos_inter).astype(np.float64)
-    relevance = sp.csr_matrix(test_interactions.multiply(pos_inter)).astype(np.float64)
-    ror.sort_indices()
-    relevance.sort_indices()
-    k_mask = np.less(ror.data, k + 1)
-    ror_at_k = np.maximum(np.multiply(ror.data, k_mask), 1)
+    """The pieces ndcg is computed from (eval.py:61-72): relevance = the positive interaction values, ror = the
+    predicted rank of each of them, k_mask = rank <= k, ror_at_k = rank inside k else 1.  All aligned entry by entry."""
+    interactions = sp.csr_matrix(test_interactions)
+    positives = sp.csr_matrix(interactions > 0)
+    ror = _ranks_of_positives(predicted_ranks, positives).astype(np.float64)
+    relevance = sp.csr_matrix(interactions.multiply(positives)).astype(np.float64)
+    for m in (ror, relevance):
+        m.sort_indices()
+    k_mask = ror.data < k + 1
+    ror_at_k = np.where(k_mask, ror.data, 1.0)
     return relevance, k_mask, ror, ror_at_k
 
 
 def _idcg(hits, k=10):
-    """eval.py:75-78."""
-    sorted_hits = hits[np.argsort(-hits)][:min(len(hits), k)]
-    return np.sum((2 ** sorted_hits - 1) / np.log2(np.arange(len(sorted_hits)) + 2))
+    """Ideal DCG of one user's relevance row (eval.py:75-78): the k largest gains at ranks 1..k."""
+    best = np.sort(np.asarray(hits))[::-1][:k]
+    return float(np.sum((np.exp2(best) - 1.0) / np.log2(np.arange(2, best.shape[0] + 2))))
 
 
 def _dcg(relevance, k_mask, ror_at_k, ror):
-    """eval.py:81-87."""
-    numer = (2 ** np.multiply(relevance.data, k_mask)) - 1
-    denom = np.log2(ror_at_k + 1)
-    ror.data = numer / denom
-    return ror.sum(axis=1).flatten()
+    """DCG per user (eval.py:81-87): sum over the positives ranked inside k of (2^relevance - 1) / log2(rank + 1);
+    returned as the reference does, a 1 x n_users matrix."""
+    gain = (np.exp2(np.where(k_mask, relevance.data, 0.0)) - 1.0) / np.log2(ror_at_k + 1.0)
+    per_entry = sp.csr_matrix((gain, ror.indices, ror.indptr), shape=ror.shape)
+    return per_entry.sum(axis=1).flatten()
 
 
 def ndcg_at_k(predicted_ranks, test_interactions, k=10, preserve_rows=False):
-    """eval.py:89-117."""
-    relevance, k_mask, ranks_of_relevant, ror_at_k = _setup_ndcg(predicted_ranks, test_interactions, k)
-    dcg = np.asarray(_dcg(relevance, k_mask, ror_at_k, ranks_of_relevant))[0]
-    idcg = np.apply_along_axis(_idcg, 1, relevance.toarray())
+    """Normalised discounted cumulative gain at k (eval.py:89-117)."""
+    relevance, k_mask, ror, ror_at_k = _setup_ndcg(predicted_ranks, test_interactions, k)
+    dcg = np.asarray(_dcg(relevance, k_mask, ror_at_k, ror)).reshape(-1)
+    ideal = np.array([_idcg(row) for row in relevance.toarray()])
     with np.errstate(divide='ignore', invalid='ignore'):
-        ndcg = dcg / idcg
-    if not preserve_rows:
-        positive_test_interactions = sp.csr_matrix(sp.csr_matrix(test_interactions) > 0)
-        ndcg = ndcg[positive_test_interactions.getnnz(axis=1) > 0]
-    return ndcg
+        ndcg = dcg / ideal
+    if preserve_rows:
+        return ndcg
+    return ndcg[np.asarray(relevance.getnnz(axis=1)).reshape(-1) > 0]
 
 
 def f1_score_at_k(predicted_ranks, test_interactions, k=10, preserve_rows=False):
-    """eval.py:120-148."""
-    p_at_k = precision_at_k(predicted_ranks=predicted_ranks, test_interactions=test_interactions, k=k,
-                            preserve_rows=preserve_rows)
-    r_at_k = recall_at_k(predicted_ranks=predicted_ranks, test_interactions=test_interactions, k=k,
-                         preserve_rows=preserve_rows)
-    mean_p, mean_r = np.mean(p_at_k), np.mean(r_at_k)
-    return (2.0 * mean_p * mean_r) / (mean_p + mean_r)
+    """Harmonic mean of the mean precision and the mean recall at k (eval.py:120-148)."""
+    mean_p = np.mean(precision_at_k(predicted_ranks, test_interactions, k=k, preserve_rows=preserve_rows))
+    mean_r = np.mean(recall_at_k(predicted_ranks, test_interactions, k=k, preserve_rows=preserve_rows))
+    return 2.0 * mean_p * mean_r / (mean_p + mean_r)
+
+
+def _mean_metrics(predicted_ranks, interactions, recall_k, precision_k, ndcg_k):
+    return (np.mean(recall_at_k(predicted_ranks, interactions, k=recall_k)),
+            np.mean(precision_at_k(predicted_ranks, interactions, k=precision_k)),
+            np.mean(ndcg_at_k(predicted_ranks, interactions, k=ndcg_k)))
 
 
 def fit_and_eval(model, user_features, item_features, train_interactions, test_interactions, fit_kwargs, recall_k=30,
                  precision_k=5, ndcg_k=30):
-    """eval.py:151-166."""
+    """Fit, rank, and report (recall, precision, ndcg) out of sample followed by the same three in sample
+    (eval.py:151-166)."""
     model.fit(user_features=user_features, item_features=item_features, interactions=train_interactions, **fit_kwargs)
     predicted_ranks = model.predict_rank(user_features=user_features, item_features=item_features)
-    p_at_k = precision_at_k(predicted_ranks, test_interactions, k=precision_k)
-    r_at_k = recall_at_k(predicted_ranks, test_interactions, k=recall_k)
-    n_at_k = ndcg_at_k(predicted_ranks, test_interactions, k=ndcg_k)
-    p_at_k_insample = precision_at_k(predicted_ranks, train_interactions, k=precision_k)
-    r_at_k_insample = recall_at_k(predicted_ranks, train_interactions, k=recall_k)
-    n_at_k_insample = ndcg_at_k(predicted_ranks, train_interactions, k=ndcg_k)
-    return (np.mean(r_at_k), np.mean(p_at_k), np.mean(n_at_k), np.mean(r_at_k_insample), np.mean(p_at_k_insample),
-            np.mean(n_at_k_insample))
+    return (_mean_metrics(predicted_ranks, test_interactions, recall_k, precision_k, ndcg_k)
+            + _mean_metrics(predicted_ranks, train_interactions, recall_k, precision_k, ndcg_k))
 
 
 def eval_random_ranks_on_dataset(interactions, recall_k=30, precision_k=5, ndcg_k=30):
-    """eval.py:181-192."""
+    """The metrics of uniformly random rankings, a floor to compare a model with (eval.py:181-192)."""
     n_users, n_items = interactions.shape
-    random_guesses = np.array([np.random.choice(a=n_items, size=n_items, replace=False) + 1 for _ in range(n_users)])
-    return (np.mean(recall_at_k(random_guesses, interactions, k=recall_k)),
-            np.mean(precision_at_k(random_guesses, interactions, k=precision_k)),
-            np.mean(ndcg_at_k(random_guesses, interactions, k=ndcg_k)))
+    random_ranks = np.stack([np.random.permutation(n_items) + 1 for _ in range(n_users)])
+    return _mean_metrics(random_ranks, interactions, recall_k, precision_k, ndcg_k)
