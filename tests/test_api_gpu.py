@@ -324,8 +324,8 @@ def test_training_matmul_runs_on_k1_and_matches_torch_sparse(T):
         assert type(out1.grad_fn).__name__.startswith('_CsrMatmul')
         (out1 * g).sum().backward()
         (out2 * g).sum().backward()
-        scale = float(out2.abs().max()) + 1e-6
-        assert float((out1 - out2).abs().max()) <= 1e-5 * scale
+        scale = float(out2.detach().abs().max()) + 1e-6
+        assert float((out1 - out2).detach().abs().max()) <= 1e-5 * scale
         assert float((w1.grad - w2.grad).abs().max()) <= 1e-5 * (float(w2.grad.abs().max()) + 1e-6)
         again = sparse_dense_matmul(tf_a, w1.detach().clone().requires_grad_(True))
         assert torch.equal(again, out1)                                           # deterministic forward
