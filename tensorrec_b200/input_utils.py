@@ -32,15 +32,46 @@ def sparse_matrix_from_tensorrec_dataset(dataset):
     return sp.coo_matrix((dataset.values, (dataset.row_index, dataset.col_index)), shape=(dataset.d0, dataset.d1))
 
 
-def _tfrecord_unavailable(*_args, **_kwargs):
-    raise NotImplementedError('TFRecord files are a TensorFlow wire format (tf.train.Example + CRC32C framing, '
-                              'tensorrec/input_utils.py:72-127); this build has no TensorFlow and does not read or '
-                              'write them (SURVEY.md 8f, rank 4)')
+_TFRECORD_KEYS = ('row_index', 'col_index', 'values', 'd0', 'd1')
 
 
-write_tfrecord_from_sparse_matrix = _tfrecord_unavailable
-write_tfrecord_from_tensorrec_dataset = _tfrecord_unavailable
-create_tensorrec_dataset_from_tfrecord = _tfrecord_unavailable
+def write_tfrecord_from_tensorrec_dataset(tfrecord_path, dataset):
+    """input_utils.py:72-103: one tf.train.Example with the five TensorRec features, framed as one TFRecord.
+    Written without TensorFlow (tfrecord.py); a list of datasets becomes one record (= one batch) each."""
+    from . import tfrecord
+    datasets = [dataset] if isinstance(dataset, TensorRecDataset) else list(dataset)
+    payloads = []
+    for ds in datasets:
+        payloads.append(tfrecord.encode_example(collections.OrderedDict([
+            ('row_index', ('int64', ds.row_index)), ('col_index', ('int64', ds.col_index)),
+            ('values', ('float', ds.values)), ('d0', ('int64', [ds.d0])), ('d1', ('int64', [ds.d1]))])))
+    return tfrecord.write_records(tfrecord_path, payloads)
+
+
+def write_tfrecord_from_sparse_matrix(tfrecord_path, sparse_matrix):
+    """input_utils.py:43-53."""
+    return write_tfrecord_from_tensorrec_dataset(
+        tfrecord_path=tfrecord_path, dataset=create_tensorrec_dataset_from_sparse_matrix(sparse_matrix=sparse_matrix))
+
+
+def create_tensorrec_dataset_from_tfrecord(tfrecord_path):
+    """input_utils.py:106-127: the records of a TFRecord file as TensorRecDatasets, one per record (the reference's
+    tf.data pipeline yields one batch per record).  Checksums are verified; a record without the five features of
+    the layout is an error."""
+    from . import tfrecord
+    datasets = []
+    for payload in tfrecord.read_records(tfrecord_path):
+        features = tfrecord.decode_example(payload)
+        missing = [key for key in _TFRECORD_KEYS if features.get(key) is None]
+        if missing:
+            raise ValueError('{}: record without the TensorRec features {}'.format(tfrecord_path, missing))
+        row, col, values = features['row_index'], features['col_index'], features['values']
+        if not (len(row) == len(col) == len(values)) or len(features['d0']) != 1 or len(features['d1']) != 1:
+            raise ValueError('{}: inconsistent feature lengths in a TensorRec record'.format(tfrecord_path))
+        datasets.append(TensorRecDataset(np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64),
+                                         np.asarray(values, dtype=np.float32), int(features['d0'][0]),
+                                         int(features['d1'][0])))
+    return datasets
 
 
 class SparseInput(object):

@@ -164,8 +164,10 @@ class TensorRec(object):
             return [wrap(v) for v in raw_input]
         if isinstance(raw_input, str) or (isinstance(raw_input, list) and raw_input and
                                           all(isinstance(v, str) for v in raw_input)):
+            # TFRecord path(s) (tensorrec.py:203-215): every record of every file is one batch
             from .input_utils import create_tensorrec_dataset_from_tfrecord
-            create_tensorrec_dataset_from_tfrecord(raw_input)   # raises NotImplementedError with the explanation
+            paths = [raw_input] if isinstance(raw_input, str) else raw_input
+            return [wrap(ds) for path in paths for ds in create_tensorrec_dataset_from_tfrecord(path)]
         raise ValueError('Input must be a scipy sparse matrix, an iterable of scipy sprase matrices, or a TensorFlow '
                          'Dataset')
 

@@ -38,8 +38,9 @@ def calculate_batched_alpha(num_batches, alpha):
 def matrices_from_raw_input(raw_input):
     """util.py:34-58 (datasets_from_raw_input): a scipy sparse matrix or a list of them -> list of matrices.
 
-    The reference also accepts tf.data.Dataset objects and TFRecord paths; both are TensorFlow wire formats, which
-    this build does not read -- they raise ValueError like any other unsupported input."""
+    The reference also accepts tf.data.Dataset objects and TFRecord paths; TensorRec's own input handling
+    (TensorRec._inputs_from_raw) takes the dataset 5-tuples and TFRecord paths (input_utils.py / tfrecord.py), this
+    helper covers the in-memory matrices."""
     if sp.issparse(raw_input):
         return [raw_input]
     if isinstance(raw_input, list) and len(raw_input) > 0 and all(sp.issparse(v) for v in raw_input):

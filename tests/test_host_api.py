@@ -209,8 +209,8 @@ def test_fit_rejects_non_sparse_input(data):
         model.fit(interactions, uf, 'not-a-matrix', epochs=1) if False else model.fit(interactions, uf, 7, epochs=1)
     with pytest.raises(BatchNonSparseInputException):
         model.fit(create_tensorrec_dataset_from_sparse_matrix(interactions), uf, itf, epochs=1, user_batch_size=2)
-    with pytest.raises(NotImplementedError):            # TFRecord paths are a TensorFlow wire format
-        model.fit('/tmp/interactions.tfrecord', uf, itf, epochs=1)
+    with pytest.raises(FileNotFoundError):              # a str is a TFRecord path (tests/test_tfrecord.py)
+        model.fit('/tmp/no-such-interactions.tfrecord', uf, itf, epochs=1)
 
 
 def test_fit_accepts_dataset_tuples(data):
