@@ -14,6 +14,9 @@ def _l2_normalize(x, eps=1e-12):
 
 def _needs_grad(*tensors):
     """True -> some input carries a gradient: differentiable torch ops (training step); False -> kernels on CUDA."""
+    from .session_management import in_training_step
+    if in_training_step():
+        return True
     for t in tensors:
         if isinstance(t, torch.Tensor):
             if t.requires_grad and torch.is_grad_enabled():
@@ -28,6 +31,23 @@ def _as_device_f32(x):
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
     return x.to(device='cuda', dtype=torch.float32).contiguous()
+
+
+def _serial_operands(tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
+    """The serial forms are part of the training step (torch ops); plain numpy arrays -- what the reference's own
+    tests pass in -- are accepted too and become tensors on the representations' device."""
+    def tensor(x, index=False, like=None):
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x))
+            if not index and x.dtype == torch.float64:
+                x = x.to(torch.float32)
+        if index:
+            x = x.to(torch.long)
+        return x.to(like.device) if like is not None else x
+
+    users = tensor(tf_user_representation)
+    items = tensor(tf_item_representation, like=users)
+    return users, items, tensor(tf_x_user, index=True, like=users), tensor(tf_x_item, index=True, like=users)
 
 
 class AbstractPredictionGraph(object):
@@ -51,9 +71,9 @@ class DotProductPredictionGraph(AbstractPredictionGraph):
         return kernels.score_exact(_as_device_f32(tf_user_representation), _as_device_f32(tf_item_representation))
 
     def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
-        gathered_user_reprs = tf_user_representation[tf_x_user]
-        gathered_item_reprs = tf_item_representation[tf_x_item]
-        return torch.sum(gathered_user_reprs * gathered_item_reprs, dim=1)
+        users, items, x_user, x_item = _serial_operands(tf_user_representation, tf_item_representation, tf_x_user,
+                                                        tf_x_item)
+        return torch.sum(users[x_user] * items[x_item], dim=1)
 
 
 class CosineSimilarityPredictionGraph(AbstractPredictionGraph):
@@ -65,9 +85,9 @@ class CosineSimilarityPredictionGraph(AbstractPredictionGraph):
         return relative_cosine(tf_tensor_1=tf_user_representation, tf_tensor_2=tf_item_representation)
 
     def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
-        normalized_users = _l2_normalize(tf_user_representation)
-        normalized_items = _l2_normalize(tf_item_representation)
-        return torch.sum(normalized_users[tf_x_user] * normalized_items[tf_x_item], dim=1)
+        users, items, x_user, x_item = _serial_operands(tf_user_representation, tf_item_representation, tf_x_user,
+                                                        tf_x_item)
+        return torch.sum(_l2_normalize(users)[x_user] * _l2_normalize(items)[x_item], dim=1)
 
 
 class EuclideanSimilarityPredictionGraph(AbstractPredictionGraph):
@@ -86,6 +106,7 @@ class EuclideanSimilarityPredictionGraph(AbstractPredictionGraph):
                                    mode=1)
 
     def connect_serial_prediction_graph(self, tf_user_representation, tf_item_representation, tf_x_user, tf_x_item):
-        delta = (tf_user_representation[tf_x_user] - tf_item_representation[tf_x_item]) ** 2
-        distance = torch.clamp(torch.sum(delta, dim=1), min=self.epsilon)
+        users, items, x_user, x_item = _serial_operands(tf_user_representation, tf_item_representation, tf_x_user,
+                                                        tf_x_item)
+        distance = torch.clamp(torch.sum((users[x_user] - items[x_item]) ** 2, dim=1), min=self.epsilon)
         return -1.0 * torch.sqrt(distance)

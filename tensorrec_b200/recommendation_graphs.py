@@ -15,6 +15,9 @@ from .session_management import get_variable
 def _needs_grad(*tensors):
     """True -> some input carries a gradient: evaluate with differentiable torch ops (the training step).
     False -> plain arrays / gradient-free tensors: evaluate with the kernels on the CUDA device (no CPU path)."""
+    from .session_management import in_training_step
+    if in_training_step():
+        return True
     for t in tensors:
         if isinstance(t, torch.Tensor):
             if t.requires_grad and torch.is_grad_enabled():
@@ -32,17 +35,35 @@ def _dev(x, dtype=torch.float32):
     return x.to(device='cuda', dtype=dtype).contiguous()
 
 
+class _DeferredProjection(object):
+    """reduce_sum(features @ biases, 1) of a graph node that is evaluated on demand (tf semantics: values assigned to
+    the bias variable after the node was built are seen)."""
+
+    def __init__(self, tf_features, tf_feature_biases):
+        self.tf_features, self.tf_feature_biases = tf_features, tf_feature_biases
+
+    def value(self):
+        return torch.sum(torch.sparse.mm(self.tf_features, self.tf_feature_biases.detach()), dim=1)
+
+    def eval(self, session=None, feed_dict=None):
+        return self.value().cpu().numpy()
+
+
 def project_biases(tf_features, n_features):
     """recommendation_graphs.py:4-19.  Returns (feature_biases [n_features, 1], projected_biases [n_rows]).
 
     tf_features: torch sparse tensor (training) or kernels.DeviceCSR / scipy matrix (prediction)."""
     from . import kernels
     if isinstance(tf_features, torch.Tensor):
+        from .session_management import in_training_step
+        from .sparse_ops import sparse_dense_matmul
         tf_feature_biases = get_variable('feature_biases_{}x{}'.format(tf_features.shape[0], n_features),
                                          lambda: torch.zeros([n_features, 1], device=tf_features.device))
-        from .sparse_ops import sparse_dense_matmul
-        projected = torch.sum(sparse_dense_matmul(tf_features, tf_feature_biases), dim=1)
-        return tf_feature_biases, projected
+        if in_training_step():
+            return tf_feature_biases, torch.sum(sparse_dense_matmul(tf_features, tf_feature_biases), dim=1)
+        # built outside a training step (the reference's own test does: build, assign bias values, THEN evaluate,
+        # test/test_recommendation_graphs.py:20-40): the projection is evaluated when it is asked for
+        return tf_feature_biases, _DeferredProjection(tf_features, tf_feature_biases)
     if sp.issparse(tf_features):
         tf_features = kernels.DeviceCSR.from_scipy(tf_features)
     tf_feature_biases = torch.zeros([n_features, 1], device='cuda')
@@ -75,12 +96,25 @@ def bias_prediction_dense(tf_prediction, tf_projected_user_biases, tf_projected_
 
 def bias_prediction_serial(tf_prediction_serial, tf_projected_user_biases, tf_projected_item_biases, tf_x_user,
                            tf_x_item):
-    """recommendation_graphs.py:44-57."""
-    return tf_prediction_serial + tf_projected_user_biases[tf_x_user] + tf_projected_item_biases[tf_x_item]
+    """recommendation_graphs.py:44-57 (training step: torch ops; numpy inputs are accepted like in the reference's
+    tests)."""
+    def tensor(x, like=None, index=False):
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x))
+        if index:
+            x = x.to(torch.long)
+        return x.to(like.device) if like is not None else x
+
+    prediction = tensor(tf_prediction_serial)
+    user_biases, item_biases = tensor(tf_projected_user_biases, prediction), tensor(tf_projected_item_biases, prediction)
+    x_user, x_item = tensor(tf_x_user, prediction, index=True), tensor(tf_x_item, prediction, index=True)
+    return prediction + user_biases[x_user].to(prediction.dtype) + item_biases[x_item].to(prediction.dtype)
 
 
 def densify_sampled_item_predictions(tf_sample_predictions_serial, tf_n_sampled_items, tf_n_users):
     """recommendation_graphs.py:60-70."""
+    if not isinstance(tf_sample_predictions_serial, torch.Tensor):
+        tf_sample_predictions_serial = torch.as_tensor(np.asarray(tf_sample_predictions_serial))
     return tf_sample_predictions_serial.reshape(int(tf_n_users), int(tf_n_sampled_items))
 
 

@@ -21,6 +21,15 @@ class Session(object):
     def is_cuda(self):
         return self.device.type == 'cuda'
 
+    def run(self, fetches, feed_dict=None):
+        """tf.Session.run for code written against the reference: nothing is deferred here, so fetching a tensor just
+        returns its value as a numpy array (lists / tuples element-wise; ops such as an initializer are None)."""
+        if isinstance(fetches, (list, tuple)):
+            return type(fetches)(self.run(f) for f in fetches)
+        if isinstance(fetches, torch.Tensor):
+            return fetches.detach().cpu().numpy()
+        return fetches
+
 
 _session = None
 
@@ -50,6 +59,22 @@ def variable_scope(store):
         yield store
     finally:
         _scope.store = previous
+
+
+@contextlib.contextmanager
+def training_step():
+    """Inside a training step every graph function evaluates with differentiable torch ops, also when no input
+    happens to carry a gradient (weight-free representation graphs): the kernel path is the predict path."""
+    previous = getattr(_scope, 'training', False)
+    _scope.training = True
+    try:
+        yield
+    finally:
+        _scope.training = previous
+
+
+def in_training_step():
+    return getattr(_scope, 'training', False)
 
 
 def get_variable(name, initializer):

@@ -210,6 +210,11 @@ class TensorRec(object):
     # training step (define-by-run form of _build_tf_graph, tensorrec.py:270-492)
     # ------------------------------------------------------------------------------------------------
     def _training_losses(self, interactions, user_features, item_features, n_sampled_items, device):
+        from .session_management import training_step
+        with training_step():
+            return self._training_losses_impl(interactions, user_features, item_features, n_sampled_items, device)
+
+    def _training_losses_impl(self, interactions, user_features, item_features, n_sampled_items, device):
         tf_user_features = user_features.torch_sparse(device)
         tf_item_features = item_features.torch_sparse(device)
         tf_interactions = interactions.torch_sparse(device)
