@@ -203,12 +203,38 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+def workload_string(args):
+    """config.workload: the same string in both arms (the driver compares them)."""
+    return ('predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, LinearRepr x DotProduct, biased '
+            '(BASELINE configs[4] shape at the size the metric is quoted on; SURVEY C5)'
+            % (args.k, args.users, args.items, args.d))
+
+
+PHASES = ['k1_users', 'items_prep', 'filter', 'rescore', 'fallback', 'exchange', 'merge']
+
+
+def oracle_topk_rows(uf, itf, wu, wi, bu, bi, rows, k, item_repr=None, item_bias=None):
+    """Reference-semantics top-k (oracle) of the given user rows against ALL items (CPU)."""
+    from oracle import reference_ops as R
+    if item_repr is None:
+        item_repr = R.sparse_dense_matmul_fast(itf, wi)
+        item_bias = np.asarray(itf @ bi, dtype=np.float32)
+    out = np.empty((len(rows), k), dtype=np.int32)
+    for c0 in range(0, len(rows), 512):
+        sub = uf[rows[c0:c0 + 512]]
+        user_repr = R.sparse_dense_matmul_fast(sub, wu)
+        user_bias = np.asarray(sub @ bu, dtype=np.float32)
+        scores = R.bias_prediction_dense(R.dot_product_dense(user_repr, item_repr), user_bias, item_bias)
+        out[c0:c0 + 512] = R.top_k_from_scores_fast(scores, k)[0]
+    return out, item_repr, item_bias
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import tensorrec_b200
     from tensorrec_b200 import kernels
-    from tensorrec_b200.distributed import shard_bounds, all_gather_candidates
+    from tensorrec_b200.distributed import shard_bounds, exchange_rows
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -225,9 +251,12 @@ def run_b200(args):
     uf, itf, wu, wi, bu, bi = make_problem(args)
     n_users, n_items, d, k = args.users, args.items, args.d, args.k
     d_pad = kernels.d_pad_for(d)
-    lo, hi = shard_bounds(n_items, world, rank)       # item axis sharded over ranks
+    # item axis sharded over ranks; --emulate-shards N times ONE shard of N on one GPU (development aid)
+    n_shards = args.emulate_shards if (world == 1 and args.emulate_shards > 1) else world
+    lo, hi = shard_bounds(n_items, n_shards, rank if world > 1 else 0)
     itf_local = itf[lo:hi]
     n_local = hi - lo
+    u_lo, u_hi = shard_bounds(n_users, world, rank)     # the user slice whose final answer this rank forms
 
     def barrier():
         if world > 1:
@@ -239,61 +268,69 @@ def run_b200(args):
     icsr = kernels.DeviceCSR.from_scipy(itf_local, device=dev)
     wu_d, wi_d = torch.from_numpy(wu).to(dev), torch.from_numpy(wi).to(dev)
     bu_d, bi_d = torch.from_numpy(bu).to(dev), torch.from_numpy(bi).to(dev)
-    ev = {'k1u': [], 'fused': []}
+    phase_events = []
 
     use_filter = args.topk_path == 'filter' and k <= kernels.filter_max_k()
-    info = {}
+    last = {}
 
     def step(record=False):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
-        if record:
-            e[0].record()
-        u32, us, usc = kernels.gather_reduce(ucsr, wu_d, want_f32=use_filter, split_d_pad=d_pad)
-        if record:
-            e[1].record()
-        i32, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=use_filter, split_d_pad=d_pad)
+        marks = []
+
+        def mark():
+            if record:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+
+        mark()
+        out = kernels.gather_reduce(ucsr, wu_d, want_f32=False, split_d_pad=d_pad, want_norm=use_filter)
+        us, usc = out[1], out[2]
+        user_norm = out[3] if use_filter else None
         ub = kernels.project_biases(ucsr, bu_d)
+        users = kernels.SideOperands(None, us, usc, ub, n_users, d, d_pad, norm=user_norm)
+        mark()
+        stats = torch.empty((3,), dtype=torch.float32, device=dev) if use_filter else None
+        _, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=False, split_d_pad=d_pad, stats=stats)
         ib = kernels.project_biases(icsr, bi_d)
-        users = kernels.SideOperands(u32, us, usc, ub, n_users, d, d_pad)
-        items = kernels.SideOperands(i32, its, isc, ib, n_local, d, d_pad)
+        items = kernels.SideOperands(None, its, isc, ib, n_local, d, d_pad, stats=stats)
         if use_filter:
-            user_norm = kernels.operand_stats(us, usc, d_pad)
-            fitems = kernels.FilterItems(items)      # stats, bias-sorted processing order, global-scale hi, bias blocks
-            if record:
-                e[2].record()
-            cs, ci, theta, flags = kernels.score_filter(us, usc, ub, user_norm, fitems.hi, fitems.stats,
-                                                        fitems.bias_pad, fitems.block_max, fitems.perm, n_users,
-                                                        n_local, d_pad, k, item_id_offset=lo)
-            if record:
-                e[3].record()
-            ts, ti, bad = kernels.rescore_topk(u32, i32, ub, ib, ci, theta, flags, user_norm, fitems.stats, k,
-                                               item_id_offset=lo)
-            # rows whose bound could not be certified go through the exact kernel (inside the timed step)
-            info['fallback_rows'] = kernels.rerun_uncertified(users, items, bad, ts, ti, k, item_id_offset=lo)
+            fitems = kernels.FilterItems(items)      # bias-sorted processing order, global-scale hi, bias blocks
+            mark()
+            _, ci, theta = kernels.score_filter(us, usc, ub, user_norm, fitems.hi, fitems.stats, fitems.bias_pad,
+                                                fitems.block_max, fitems.perm, n_users, n_local, d_pad, k,
+                                                item_id_offset=lo, block_bias_min=fitems.block_min)
+            mark()
+            top, bad = kernels.rescore_topk(users, items, ci, theta, user_norm, fitems.stats, k, item_id_offset=lo)
+            mark()
+            # rows whose bound could not be certified go through the exact kernel, routed on the device
+            counters, cap = kernels.rerun_uncertified(users, items, bad, top, k, item_id_offset=lo)
+            last['counters'], last['cap'], last['bad'] = counters, cap, bad
         else:
             meta = kernels.pack_item_meta(isc, ib, n_local)
-            if record:
-                e[2].record()
+            mark()
             cs, ci = kernels.score_topk(us, usc, ub, its, meta, n_users, n_local, d_pad, k, item_id_offset=lo)
-            if record:
-                e[3].record()
-            ts, ti = kernels.topk_merge(cs, ci, k)
+            mark()
+            top = kernels.topk_merge(cs, ci, k)
+            mark()
+        mark()
         if world > 1:
-            gs, gi = all_gather_candidates(ts, ti)
-            ts, ti = kernels.topk_merge(gs, gi, k)
+            recv, _ = exchange_rows(top.buf)
+            mark()
+            top = kernels.topk_merge_received(recv, u_hi - u_lo, world, k)
+        else:
+            mark()
+        mark()
         if record:
-            ev['k1u'].append((e[0], e[1]))
-            ev['fused'].append((e[2], e[3]))
-        return ts, ti
+            phase_events.append(marks)
+        return top
 
     n_splits = kernels.default_splits(n_users, n_local)
-    launches_per_step = (10 if use_filter else 7) + (1 if world > 1 else 0)
 
     for _ in range(args.warmup):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches_before = tensorrec_b200._lib.launch_count
@@ -304,23 +341,47 @@ def run_b200(args):
     barrier()
     gpu_launches = tensorrec_b200._lib.launch_count - launches_before   # kernel-launching C-ABI calls, counted
     ms_total = start.elapsed_time(end)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = (sampler.stop() if not args.no_clocks else {'sm_mhz': None, 'reasons': ['sampling disabled']}) \
+        if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = n_users * float(n_items) / (ms_step * 1e-3)
-    fused_ms = float(np.mean([a.elapsed_time(b) for a, b in ev['fused']]))
-    k1u_ms = float(np.mean([a.elapsed_time(b) for a, b in ev['k1u']]))
-    top_items_value = out[1][:4].cpu().numpy()
-    top_items_check = out[1][:1024].cpu().numpy()      # compared with the CPU oracle's ranking below (rank 0)
+    # whole job: all users x all items; --emulate-shards times ONE shard's pairs (development aid, not a bench value)
+    pairs = n_users * float(n_local if (world == 1 and n_shards > 1) else n_items)
+    value = pairs / (ms_step * 1e-3)
+    # per-phase device time of this rank (means over the timed steps)
+    phase_ms = np.zeros(len(PHASES))
+    for marks in phase_events:
+        for j in range(len(PHASES)):
+            phase_ms[j] += marks[j].elapsed_time(marks[j + 1])
+    phase_ms /= max(1, len(phase_events))
+    fused_ms = float(phase_ms[PHASES.index('filter')])
+    k1u_ms = float(phase_ms[PHASES.index('k1_users')])
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, phase_ms.tolist())
+        all_phase = np.asarray(gathered)
+    else:
+        all_phase = phase_ms[None, :]
+    n_check = min(args.parity_users, u_hi - u_lo)
+    top_items_check = out.items[:n_check].cpu().numpy()      # compared with the CPU oracle's ranking below (rank 0)
+    top_items_value = out.items[:4].cpu().numpy()
+    fallback_rows, fallback_ids, fallback_items = 0, np.zeros(0, np.int64), None
+    if use_filter:
+        fallback_rows = int(last['counters'][0])
+        bad_ids = torch.nonzero(last['bad'], as_tuple=True)[0]
+        bad_ids = bad_ids[(bad_ids >= u_lo) & (bad_ids < u_hi)][:args.parity_fallback_rows]
+        fallback_ids = bad_ids.cpu().numpy()
+        fallback_items = out.items[bad_ids - u_lo].cpu().numpy()
 
     # ---- e2e: the public API with host buffers ----------------------------------------------------------
     def pinned_csr(m):
         arrs = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (m.data, m.indices, m.indptr)]
         return sp.csr_matrix((arrs[0].numpy(), arrs[1].numpy(), arrs[2].numpy()), shape=m.shape), arrs
 
-    del ucsr, icsr
+    del ucsr, icsr, out
+    last.clear()
     tensorrec_b200.tensorrec.TOPK_PATH = 'auto' if use_filter else 'exact'
     model = tensorrec_b200.TensorRec(n_components=d)
     model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
@@ -330,7 +391,8 @@ def run_b200(args):
     group = dist.group.WORLD if world > 1 else None
 
     def e2e_step():
-        return model.predict_top_k(uf_host, itf_host, k, item_id_offset=lo, gather_group=group)
+        return model.predict_top_k(uf_host, itf_host, k, item_id_offset=lo, gather_group=group, gather='slice',
+                                   user_batch_size=args.user_batch)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -349,9 +411,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_step = float(t.item()) / args.steps
-    e2e_value = n_users * float(n_items) / (e2e_ms_step * 1e-3)
+    e2e_value = pairs / (e2e_ms_step * 1e-3)
     h2d = 4 * (uf.nnz * 2 + uf.shape[0] + 1 + itf_local.nnz * 2 + itf_local.shape[0] + 1)
-    d2h = n_users * k * 8
+    d2h = n_users * k * 8      # whole job: every rank reads back the top-k of ITS user slice
     same = bool(np.array_equal(top.items[:4], top_items_value))
 
     if rank != 0:
@@ -363,37 +425,54 @@ def run_b200(args):
     flops = 2.0 * n_users * n_local * d                        # algorithmic flops of one fused launch (this rank)
     achieved = flops / (fused_ms * 1e-3) / 1e12
     peak = peaks['tflops_sustained']
-    # K1 (users) algorithmic bytes: nnz*8 + (R+1)*4 + D*d*4 + R*(2*d_pad*2 + 4) [+ R*d*4]  (D = distinct columns)
+    # K1 (users) algorithmic bytes, SURVEY 8(d): nnz*8 + (R+1)*4 + D*d*4 (each DISTINCT weight row once) + R*d*4 (the
+    # output: here the split operand, hi + lo fp16 = 4 bytes per component, + 8 bytes of scale and norm per row)
     distinct = int(np.unique(uf.indices).shape[0])
-    k1_bytes = (uf.nnz * 8 + (n_users + 1) * 4 + distinct * d * 4 + n_users * (2 * d_pad * 2 + 4)
-                + (n_users * d * 4 if use_filter else 0))      # the filter path also writes the fp32 representation
-    k1_gbs = k1_bytes / (k1u_ms * 1e-3) / 1e9
+    k1_bytes = uf.nnz * 8 + (n_users + 1) * 4 + distinct * d * 4 + n_users * (2 * d_pad * 2 + 8)
+    k1_survey_bytes = uf.nnz * 8 + (n_users + 1) * 4 + distinct * d * 4 + n_users * d * 4
+    # the k1_users phase also holds project_biases (one more pass over the CSR arrays): charge the phase, report both
+    k1_gbs = k1_survey_bytes / (k1u_ms * 1e-3) / 1e9
 
     cores = os.cpu_count() or 1
     cpu_value, cpu_desc, cpu_s, cpu_top = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, args.cpu_budget, cores)
-    # parity at the full item count: the reference-semantics ranking of the first users (oracle, CPU) against the GPU
-    # top-k of the same users; only sub-tolerance near-ties may order differently (fp32 rounding of the two GEMMs)
-    n_chk = min(cpu_top.shape[0], top_items_check.shape[0])
-    agree = float((cpu_top[:n_chk] == top_items_check[:n_chk]).mean()) if n_chk else None
-    same_sets = float(np.mean([set(cpu_top[i]) == set(top_items_check[i]) for i in range(n_chk)])) if n_chk else None
+    # parity at the full item count: the reference-semantics ranking (oracle, CPU) of the first users of this rank's
+    # slice AND of the rows the certificate rejected in the last step, against the GPU top-k of the same users; only
+    # sub-tolerance near-ties may order differently (fp32 rounding of the two GEMMs)
+    t0 = time.perf_counter()
+    rows = np.concatenate([np.arange(u_lo, u_lo + n_check), fallback_ids]).astype(np.int64)
+    exp, _, _ = oracle_topk_rows(uf, itf, wu, wi, bu, bi, rows, k)
+    got = np.concatenate([top_items_check, fallback_items]) if len(fallback_ids) else top_items_check
+    agree = float((exp == got).mean()) if len(rows) else None
+    same_sets = float(np.mean([set(exp[i]) == set(got[i]) for i in range(len(rows))])) if len(rows) else None
+    fb_agree = float((exp[n_check:] == got[n_check:]).mean()) if len(fallback_ids) else None
+    # the double-argsort oracle of the cpu_baseline leg ranks the same first users: its top-k must equal the fast oracle's
+    n_dbl = min(cpu_top.shape[0], n_check)
+    oracle_self = bool(np.array_equal(cpu_top[:n_dbl], exp[:n_dbl])) if (n_dbl and u_lo == 0) else None
+    log('[bench] parity check on %d users in %.1fs' % (len(rows), time.perf_counter() - t0))
 
+    def phase_table(col):
+        return {name: round(float(col[j]), 4) for j, name in enumerate(PHASES)}
+
+    rest_ms = ms_step - fused_ms
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': ('f32 (1 fp16 tcgen05 filter pass with a certified bound + exact fp32 re-scoring of the survivors)'
+        'dtype': ('f32 (1 fp16 tcgen05 filter pass with a certified bound + re-scoring of the survivors from the 22-bit '
+                  'split operands, fp32 accumulate)'
                   if use_filter else 'f32 (3 x fp16 split-product tcgen05 passes, fp32 accumulate)'),
         'data': 'synthetic',
-        'config': {'workload': 'predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, '
-                               'LinearRepr x DotProduct, biased (BASELINE configs[4] shape at 1M x 1M; SURVEY C5)'
-                               % (k, n_users, n_items, d),
-                   'parallelism': 'item-sharded x%d + 1 NCCL all-gather' % world if world > 1 else 'single GPU',
+        'config': {'workload': workload_string(args),
+                   'parallelism': ('item-sharded x%d: 1 NCCL all-to-all of the per-shard top-k, each rank merges its '
+                                   'user slice' % world) if world > 1 else 'single GPU',
                    'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
-                   'fallback_rows_last_step': info.get('fallback_rows', 0), 'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
+                   'fallback_rows_last_step': fallback_rows,
+                   'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
                    % ((n_users + n_local) * 2 * d_pad * 2 / 1e6, (wu.nbytes + wi.nbytes) / 1e6)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_ms_step, 'api': 'TensorRec.predict_rank(user_features, item_features, k) on pinned '
-                'host CSR', 'matches_value_arm': same},
+                'host CSR' + ('; every rank reads back its user slice' if world > 1 else ''),
+                'matches_value_arm': same},
         'gpu_launches': int(gpu_launches),
         'roofline': {'kernel': ('score_filter_kernel (trk_score_filter_f16)' if use_filter
                                 else 'score_tc_kernel<topk> (trk_score_topk_f16x3)'), 'bound': 'tensor',
@@ -403,18 +482,49 @@ def run_b200(args):
                      'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'ms_per_launch': fused_ms,
                      'issued_tflops': (1 if use_filter else 3) * achieved,
                      'issued_frac': (1 if use_filter else 3) * achieved / peak, 'share_of_step': fused_ms / ms_step},
-        'roofline_k1': {'kernel': 'csr_gather_reduce_kernel (users)', 'bound': 'hbm', 'achieved': k1_gbs,
-                        'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k1_gbs / peaks['hbm_gbs'],
-                        'ms_per_launch': k1u_ms, 'algorithmic_bytes': int(k1_bytes)},
+        'roofline_k1': {'kernel': 'csr_gather_reduce_kernel (users) + csr_project_biases_kernel', 'bound': 'hbm',
+                        'achieved': k1_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': k1_gbs / peaks['hbm_gbs'],
+                        'ms_per_launch': k1u_ms, 'algorithmic_bytes': int(k1_survey_bytes),
+                        'bytes_with_scale_and_norm': int(k1_bytes),
+                        'traffic': ncu_traffic('csr_gather_reduce_kernel@%dx%d' % (n_users, d))},
+        'phases_ms': {'rank0': phase_table(phase_ms), 'max_over_ranks': phase_table(all_phase.max(axis=0)),
+                      'mean_over_ranks': phase_table(all_phase.mean(axis=0)),
+                      'unsharded_share_of_step': rest_ms / ms_step if world > 1 or n_shards > 1 else None},
         'cpu_baseline': {'value': cpu_value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc,
                          'seconds': cpu_s},
-        'parity': {'users_checked': int(n_chk), 'items': int(n_items), 'rank_positions_equal': agree,
-                   'topk_sets_equal': same_sets,
-                   'against': 'oracle (numpy restatement of the reference: fp32 GEMM + double stable argsort)'},
+        'parity': {'users_checked': int(n_check), 'fallback_rows_checked': int(len(fallback_ids)),
+                   'items': int(n_items), 'rank_positions_equal': agree, 'topk_sets_equal': same_sets,
+                   'fallback_rank_positions_equal': fb_agree, 'double_argsort_oracle_agrees': oracle_self,
+                   'against': 'oracle (numpy restatement of the reference: fp32 GEMM + bias adds + rank<=k in '
+                              'tf.nn.top_k order)'},
     }
+    if world == 1 and n_shards > 1:
+        result['emulated_shard'] = '1 of %d (development aid: one shard timed alone, no exchange)' % n_shards
+    if world == 1 and n_shards == 1 and not args.no_extra:
+        del model, uf_host, itf_host, _keep_u, _keep_i, wu_d, wi_d
+        torch.cuda.empty_cache()
+        result['extra'] = run_extras(args)
     print(json.dumps(result), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args):
+    """Secondary workloads measured in the same default run (N = 1) so that they are driver-run too: each entry is the
+    JSON object the corresponding --workload prints."""
+    import copy
+    extras = {}
+    for name, fn, over in (('dense', run_dense, {'users': 65536, 'items': 100000, 'd': 64}),
+                           ('ranks', run_full_ranks, {'users': 8192, 'items': 131072, 'd': 128})):
+        a = copy.copy(args)
+        for key, val in over.items():
+            setattr(a, key, val)
+        a.steps, a.warmup = 3, 2
+        try:
+            extras[name] = fn(a, emit=False)
+        except Exception as exc:      # a secondary line must not take the headline down
+            extras[name] = {'error': repr(exc)}
+    return extras
 
 
 # ----------------------------------------------------------------------------------------------------- reference arm
@@ -437,17 +547,17 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, LinearRepr x '
-                               'DotProduct, biased' % (args.k, args.users, args.items, args.d),
-                   'note': 'numpy/scipy restatement of the reference TF-CPU semantics (TensorFlow is not installable '
-                           'here); each step is a bounded user sample of the workload'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+        'config': {'workload': workload_string(args)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': desc + ' -- numpy/scipy restatement of the reference TF-CPU semantics (TensorFlow is '
+                         'not installable here); each step is a bounded user sample of the workload, ms_per_step is the '
+                         'time of that sample'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }), flush=True)
 
 
-def run_dense(args):
+def run_dense(args, emit=True):
     """Secondary measurement (BASELINE configs[1] shape, scaled to fit HBM): predict() = K1 x2 + biases + the tensor-core
     score kernel writing the dense fp32 matrix.  Bound: HBM write, U*I*4 bytes."""
     import torch
@@ -488,16 +598,21 @@ def run_dense(args):
     kms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     peaks = measured_peaks()
     gbs = args.users * float(args.items) * 4 / (kms * 1e-3) / 1e9
-    print(json.dumps({'metric': 'predict_pairs_per_s', 'value': args.users * float(args.items) / (ms * 1e-3),
-                      'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-                      'config': {'workload': 'predict() dense fp32 scores, %d users x %d items, d=%d (BASELINE configs[1] '
-                                             'shape, user axis cut to fit HBM)' % (args.users, args.items, args.d)},
-                      'roofline': {'kernel': 'score_tc_kernel<dense>', 'bound': 'hbm', 'achieved': gbs,
-                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
-                                   'ms_per_launch': kms}}), flush=True)
+    result = {'metric': 'predict_pairs_per_s', 'value': args.users * float(args.items) / (ms * 1e-3),
+              'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+              'config': {'workload': 'predict() dense fp32 scores, %d users x %d items, d=%d (BASELINE configs[1] '
+                                     'shape, user axis cut to fit HBM)' % (args.users, args.items, args.d)},
+              'roofline': {'kernel': 'score_tc_kernel<dense>', 'bound': 'hbm', 'achieved': gbs,
+                           'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+                           'ms_per_launch': kms}}
+    del out
+    torch.cuda.empty_cache()
+    if emit:
+        print(json.dumps(result), flush=True)
+    return result
 
 
-def run_full_ranks(args):
+def run_full_ranks(args, emit=True):
     """Secondary measurement: predict_rank() in the reference's full mode -- dense scores, then the exact int32 rank of
     every (user, item) pair (rank_predictions, tensorrec/recommendation_graphs.py:73-82) -- at a shape whose [U, I]
     matrices fit HBM.  Bound: HBM (the score matrix is written once, read by the chunk sort, the sorted keys are
@@ -552,14 +667,18 @@ def run_full_ranks(args):
     pairs = args.users * float(args.items)
     alg_bytes = pairs * (4 + 4)        # scores read once, ranks written once
     gbs = alg_bytes / (kms * 1e-3) / 1e9
-    print(json.dumps({'metric': 'predict_rank_full_ranks_per_s', 'value': pairs / (ms * 1e-3), 'unit': 'ranks/s',
-                      'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-                      'config': {'workload': 'predict_rank() full int32 ranks, %d users x %d items, d=%d (reference '
-                                             'semantics: every pair ranked)' % (args.users, args.items, args.d)},
-                      'roofline': {'kernel': 'rank_chunk_sort_kernel + rank_merge_pass_kernel (trk_rank_full)',
-                                   'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                   'frac': gbs / peaks['hbm_gbs'], 'ms_per_launch': kms,
-                                   'ranks_per_s_kernel': pairs / (kms * 1e-3)}}), flush=True)
+    result = {'metric': 'predict_rank_full_ranks_per_s', 'value': pairs / (ms * 1e-3), 'unit': 'ranks/s',
+              'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+              'config': {'workload': 'predict_rank() full int32 ranks, %d users x %d items, d=%d (reference '
+                                     'semantics: every pair ranked)' % (args.users, args.items, args.d)},
+              'roofline': {'kernel': 'trk_rank_full', 'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'],
+                           'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'ms_per_launch': kms,
+                           'ranks_per_s_kernel': pairs / (kms * 1e-3)}}
+    del out, ranks
+    torch.cuda.empty_cache()
+    if emit:
+        print(json.dumps(result), flush=True)
+    return result
 
 
 def main():
@@ -575,6 +694,14 @@ def main():
     ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
+    ap.add_argument('--parity-users', type=int, default=4096, help='users checked against the oracle at full size')
+    ap.add_argument('--parity-fallback-rows', type=int, default=1024,
+                    help='rows rejected by the certificate (last step) that are also checked against the oracle')
+    ap.add_argument('--user-batch', type=int, default=None, help='user_batch_size of the API (e2e) arm')
+    ap.add_argument('--emulate-shards', type=int, default=1,
+                    help='development aid (1 GPU): time the work of ONE item shard out of this many, no exchange')
+    ap.add_argument('--no-clocks', action='store_true', help='do not sample nvidia-smi during the timed region')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads of the default run')
     args = ap.parse_args()
     if args.workload == 'dense':
         run_dense(args)

@@ -55,12 +55,17 @@ const char* trk_last_error(void);
  *                                  hi = fp16(x * 2^e_r), columns [d_pad, 2*d_pad) hold lo = fp16(x * 2^e_r - hi),
  *                                  zero padded from d to d_pad (d_pad a multiple of 64);
  *   out_scale [rows]               2^-e_r, the exact power of two that undoes the per-row scaling
- *                                  (required when out_split is given).
+ *                                  (required when out_split is given);
+ *   out_norm  [rows] (optional)    |out[r, :]|_2 inflated by 2^-9: an UPPER bound, the factor of the filter's error bound;
+ *   stats     [3]    (optional)    zeroed by this call, then stats[0] = max out_norm, stats[1] = max out_scale over the
+ *                                  non-zero rows (atomic max on the float bits: order independent); stats[2] is left
+ *                                  for trk_pack_item_bias.  The row is still in registers when these are formed: the
+ *                                  separate pass of trk_operand_stats over the operand is not needed after K1.
  * ---------------------------------------------------------------------------------------------------- */
 int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const float* val,
                               const float* weights, int64_t rows, int32_t n_features, int32_t d,
                               int32_t n_normalize, float* out_f32, void* out_split, int32_t d_pad,
-                              float* out_scale, void* stream);
+                              float* out_scale, float* out_norm, float* stats, void* stream);
 
 /* Converts an existing dense fp32 representation [rows, d] into the split-fp16 operand + scales
  * (same layout as above).  Used when a representation comes from a user-defined plugin graph. */
@@ -134,6 +139,9 @@ int trk_rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t 
  * item_meta [n_items_padded256, 2] f32 = {item scale, item bias} per item, rows beyond n_items = {0, -inf}
  * (build with trk_pack_item_meta).  user_bias may be NULL.
  * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_topk_max_k(d_pad).
+ * n_users_live (device int32, may be NULL): only the first *n_users_live user rows hold work -- user blocks beyond
+ * them are skipped on the device.  This is how the rows the filter's certificate rejects are re-scored without a
+ * host round trip (their count exists only on the device, see trk_select_flagged_rows).
  * ---------------------------------------------------------------------------------------------------- */
 int trk_score_topk_max_k(int32_t d_pad);
 int trk_pack_item_meta(const float* item_scale, const float* item_bias, int64_t n_items, float* item_meta,
@@ -141,18 +149,21 @@ int trk_pack_item_meta(const float* item_scale, const float* item_bias, int64_t 
 int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
                          const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
                          int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset,
-                         float* cand_score, int32_t* cand_item, void* stream);
+                         float* cand_score, int32_t* cand_item, const int32_t* n_users_live, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K2+K3 fused, FILTER form (the throughput path of predict_rank(k)): one tensor-core pass over the fp16 "hi"
  * halves gives approximate scores with a proven error bound m = 1.5*2^-10 * |u|_2 * max_j |i_j|_2 (+ bias
- * rounding); per user the kernel keeps every item whose approximate score is within 3m of the running k-th best.
- * trk_rescore_topk_f32 then scores the survivors exactly (fp32 dot product of the fp32 representations + biases,
- * i.e. the reference arithmetic of tensorrec/prediction_graphs.py:49-50 and recommendation_graphs.py:41), ranks
- * them in tf.nn.top_k order (recommendation_graphs.py:81) and verifies the bound; users it flags must be re-run
- * through trk_score_topk_f16x3.  Same reference chain as trk_score_topk_f16x3, one third of its tensor work.
+ * rounding); per user the kernel keeps every item whose approximate score is within 2.25 m of the running k-th best.
+ * trk_rescore_topk_split then scores the survivors from the full split operands (22-bit operands, fp32 accumulate: the
+ * arithmetic of trk_score_topk_f16x3; reference chain tensorrec/prediction_graphs.py:49-50 and
+ * recommendation_graphs.py:41), ranks them in tf.nn.top_k order (recommendation_graphs.py:81) and verifies the
+ * bound; users it flags are re-run through trk_score_topk_f16x3 (device-side routing below).  Same reference chain
+ * as trk_score_topk_f16x3, one third of its tensor work.
  *
  * Preparation (all device-side, no host sync):
+ *   K1 (trk_csr_gather_reduce_f32) already yields the user norms and the item statistics; for operands that do not
+ *   come from K1 (user-defined representation graphs):
  *   trk_operand_stats      norm[r] = |row r|_2 (upper bound) of a split operand; stats[0] = max norm, stats[1] = max
  *                          row scale, both by atomic max (stats[3] must be zeroed by the caller; either output may be
  *                          NULL)
@@ -160,14 +171,16 @@ int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const 
  *                          order: out_hi[p, :] (f16 [rows, d_pad]) = hi[perm[p], :] * (scale[perm[p]] / stats[1]) (exact
  *                          power-of-two factors; perm NULL = identity)
  *   trk_pack_item_bias     out[p] = bias[perm[p]], padded with -inf to n_padded (multiple of 256) entries; stats[2] =
- *                          max |bias|; block_max[b] = max bias of positions [128 b, 128 b + 128)
+ *                          max |bias|; block_max[b] / block_min[b] = max / min bias of positions [128 b, 128 b + 128)
+ *                          (min = -inf as soon as the block holds padding; block_min may be NULL)
  * Processing order: the host sorts the items by DESCENDING bias (perm = stable argsort) so that the biases inside a
  * 128-item block are nearly equal and the running k-th best rises early; the kernel's hot loop then bounds
- * acc_j + bias_j / c by max_j acc_j + block_max / c and touches neither the biases nor an FFMA per score.  Candidate
- * ids are reported in ORIGINAL numbering.
+ * acc_j + bias_j / c by max_j acc_j + block_max / c and touches neither the biases nor an FFMA per score.  With
+ * block_bias_min the kernel also starts every (user, split) sweep from a threshold derived from the first tile
+ * (k-th largest of 16 group maxima + block minimum) instead of -inf.  Candidate ids are reported in ORIGINAL numbering.
  * Filter outputs, one list per (user, split): cand_* [n_users, n_splits, 16] (approximate score, global id;
- * unused = (-inf, INT32_MAX)), row_theta / row_flags [n_users, n_splits].
- * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_filter_max_k(); n_components <= 128 for the rescoring.
+ * unused = (-inf, INT32_MAX)), row_theta [n_users, n_splits].
+ * Constraints: d_pad in {64, 128}; 1 <= k <= trk_score_filter_max_k().
  * ---------------------------------------------------------------------------------------------------- */
 int trk_score_filter_max_k(void);
 int trk_score_filter_list_width(void); /* candidates per list: 16 (one list per (user, split)) */
@@ -176,20 +189,39 @@ int trk_operand_stats(const void* split, const float* scale, int64_t rows, int32
 int trk_rescale_hi_global(const void* split, const float* scale, const float* stats, const int32_t* perm,
                           int64_t rows, int32_t d_pad, void* out_hi, void* stream);
 int trk_pack_item_bias(const float* item_bias, const int32_t* perm, int64_t n_items, float* out,
-                       int64_t n_items_padded, float* stats, float* block_max, void* stream);
+                       int64_t n_items_padded, float* stats, float* block_max, float* block_min, void* stream);
 int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                          const float* user_norm, const void* item_hi_global, const float* item_stats,
-                         const float* item_bias_padded, const float* block_bias_max, const int32_t* item_perm,
-                         int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
-                         int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
-                         int32_t* row_flags, void* stream);
-/* item_repr holds the rows of THIS shard: global id g lives at row g - item_id_offset.  n_lists = n_splits,
- * list_width = 16.  out_flag[u] = 1 -> re-run user u through the exact kernel. */
-int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,
-                         const float* item_bias, const int32_t* cand_item, const float* row_theta,
-                         const int32_t* row_flags, const float* user_norm, const float* item_stats, int64_t n_users,
-                         int64_t n_items_local, int32_t d, int32_t n_lists, int32_t list_width, int32_t k,
-                         int32_t item_id_offset, float* out_score, int32_t* out_item, int32_t* out_flag, void* stream);
+                         const float* item_bias_padded, const float* block_bias_max, const float* block_bias_min,
+                         const int32_t* item_perm, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
+                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
+                         float* row_theta, void* stream);
+/* item_split / item_scale / item_bias hold the rows of THIS shard: global id g lives at row g - item_id_offset.
+ * n_lists = n_splits, list_width = 16.  Row u of the result is written at out_score + u * out_row_stride and
+ * out_item + u * out_row_stride (both may point into one [n_users, 2k] exchange buffer: stride 2k, out_item =
+ * out_score + k).  out_flag[u] = 1 -> user u must be re-run through the exact kernel. */
+int trk_rescore_topk_split(const void* user_split, const float* user_scale, const void* item_split,
+                           const float* item_scale, const float* user_bias, const float* item_bias,
+                           const int32_t* cand_item, const float* row_theta, const float* user_norm,
+                           const float* item_stats, int64_t n_users, int64_t n_items_local, int32_t d_pad,
+                           int32_t n_lists, int32_t list_width, int32_t k, int32_t item_id_offset, float* out_score,
+                           int32_t* out_item, int64_t out_row_stride, int32_t* out_flag, void* stream);
+
+/* Device-side routing of the flagged users (no host round trip):
+ *   trk_select_flagged_rows  idx[0 .. min(count, capacity)) = rows with flags != 0 (any order), counters[0] = count
+ *                            (counters: int32[2], zeroed by this call; count > capacity = overflow, the host layer
+ *                            checks it at its next natural synchronisation and re-runs the whole batch exactly);
+ *   trk_gather_operand_rows  sub_split / sub_scale / sub_bias [capacity, ...] = the selected rows of a split operand;
+ *   trk_score_topk_f16x3 + trk_topk_merge with n_users_live = counters re-score exactly those rows;
+ *   trk_scatter_topk_rows    out[idx[i]] = sub[i] for i < min(count, capacity) (row i of sub_* at i * sub_row_stride). */
+int trk_select_flagged_rows(const int32_t* flags, int64_t n, int32_t* idx, int32_t capacity, int32_t* counters,
+                            void* stream);
+int trk_gather_operand_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const void* split,
+                            const float* scale, const float* bias, int32_t d_pad, void* sub_split, float* sub_scale,
+                            float* sub_bias, void* stream);
+int trk_scatter_topk_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const float* sub_score,
+                          const int32_t* sub_item, int64_t sub_row_stride, int32_t k, float* out_score,
+                          int32_t* out_item, int64_t out_row_stride, void* stream);
 
 /* Tensor-core dense prediction with the same operands, writing the full fp32 matrix out[n_users, n_items]
  * (predict(); tensorrec/tensorrec.py:636-664).  HBM-write bound. */
@@ -198,11 +230,15 @@ int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const
                           int32_t d_pad, float* out, int64_t out_row_stride, void* stream);
 
 /* Merges n_lists candidate lists per user (each sorted by (score desc, id asc), k_in entries) into the global
- * top k_out per user, same order.  Lists are the n_splits of one GPU and/or the shards gathered from the
- * other GPUs (item-axis sharding; the exchange itself is one NCCL all-gather done by the host layer).
- *   cand_* [n_users, n_lists, k_in]  ->  out_* [n_users, k_out] */
+ * top k_out per user, same order.  Lists are the n_splits of one GPU and/or the shards received from the other GPUs
+ * (item-axis sharding; the exchange itself is one NCCL all-to-all done by the host layer).
+ * Entry j of list l of user u is read at cand_*[u * user_stride + l * list_stride + j]:
+ *   one GPU, [n_users, n_lists, k_in]:                user_stride = n_lists * k_in, list_stride = k_in;
+ *   exchange receive buffer [n_lists, n_users, 2k]:   user_stride = 2k, list_stride = n_users * 2k, cand_item = cand_score + k.
+ * Row u of the result goes to out_*[u * out_row_stride ...].  n_users_live: see trk_score_topk_f16x3. */
 int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
-                   int32_t k_in, int32_t k_out, float* out_score, int32_t* out_item, void* stream);
+                   int32_t k_in, int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score,
+                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, void* stream);
 
 #ifdef __cplusplus
 }

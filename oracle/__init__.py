@@ -39,6 +39,7 @@ from .reference_ops import (  # noqa: F401
     rank_predictions,
     rank_predictions_closed_form,
     top_k_from_scores,
+    top_k_from_scores_fast,
     predict,
     predict_rank,
     predict_similar_items,

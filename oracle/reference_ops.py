@@ -200,6 +200,26 @@ def top_k_from_scores(prediction, k):
     return order, np.take_along_axis(p, order, axis=1)
 
 
+def top_k_from_scores_fast(prediction, k):
+    """Same result as top_k_from_scores without sorting whole rows: an argpartition finds the k-th best score, every
+    entry >= it is kept and those few are ordered by (score descending, index ascending) -- the order the reference's
+    double tf.nn.top_k (recommendation_graphs.py:81-82) gives the entries with rank <= k.  Checked against
+    top_k_from_scores in tests/test_oracle.py; used where the oracle ranks thousands of users against 1M items."""
+    p = np.asarray(prediction, dtype=F32)
+    n_rows, n_cols = p.shape
+    k = min(int(k), n_cols)
+    ids = np.empty((n_rows, k), dtype=np.int32)
+    vals = np.empty((n_rows, k), dtype=F32)
+    for r in range(n_rows):
+        row = p[r]
+        kth = np.partition(row, n_cols - k)[n_cols - k]           # the k-th largest value
+        cand = np.nonzero(row >= kth)[0]                          # ascending indices, >= k of them (ties at the k-th)
+        order = np.lexsort((cand, -row[cand].astype(np.float64)))[:k]
+        ids[r] = cand[order]
+        vals[r] = row[cand[order]]
+    return ids, vals
+
+
 # ---------------------------------------------------------------------------------------------------
 # a10: composition -- tensorrec/tensorrec.py:307-313, 339-346, 380-383, 406-410, 421-435, 454
 # ---------------------------------------------------------------------------------------------------

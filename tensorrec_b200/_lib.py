@@ -26,7 +26,7 @@ SIGNATURES = {
     'trk_version': (ctypes.c_int, []),
     'trk_last_error': (ctypes.c_char_p, []),
     'trk_csr_gather_reduce_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i32, _c_i32, _c_i32, _c_p, _c_p,
-                                                 _c_i32, _c_p, _c_p]),
+                                                 _c_i32, _c_p, _c_p, _c_p, _c_p]),
     'trk_split_f32_to_f16x2': (ctypes.c_int, [_c_p, _c_i64, _c_i32, _c_i32, _c_p, _c_i32, _c_p, _c_p]),
     'trk_l2_normalize_rows_f32': (ctypes.c_int, [_c_p, _c_i64, _c_i32, _c_p]),
     'trk_csr_project_biases_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p]),
@@ -38,19 +38,23 @@ SIGNATURES = {
     'trk_score_topk_max_k': (ctypes.c_int, [_c_i32]),
     'trk_pack_item_meta': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p]),
     'trk_score_topk_f16x3': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,
-                                            _c_i32, _c_p, _c_p, _c_p]),
+                                            _c_i32, _c_p, _c_p, _c_p, _c_p]),
     'trk_score_dense_f16x3': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32, _c_p, _c_i64,
                                              _c_p]),
-    'trk_topk_merge': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p]),
+    'trk_topk_merge': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_i32, _c_i32, _c_i32, _c_i64, _c_i64, _c_p, _c_p, _c_i64,
+                                      _c_p, _c_p]),
     'trk_score_filter_max_k': (ctypes.c_int, []),
     'trk_score_filter_list_width': (ctypes.c_int, []),
     'trk_operand_stats': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p, _c_p]),
     'trk_rescale_hi_global': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p]),
-    'trk_pack_item_bias': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p]),
-    'trk_score_filter_f16': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32,
-                                            _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
-    'trk_rescore_topk_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32,
+    'trk_pack_item_bias': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p, _c_p, _c_p, _c_p]),
+    'trk_score_filter_f16': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64,
                                             _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p]),
+    'trk_rescore_topk_split': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64,
+                                              _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_i64, _c_p, _c_p]),
+    'trk_select_flagged_rows': (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_i32, _c_p, _c_p]),
+    'trk_gather_operand_rows': (ctypes.c_int, [_c_p, _c_p, _c_i32, _c_p, _c_p, _c_p, _c_i32, _c_p, _c_p, _c_p, _c_p]),
+    'trk_scatter_topk_rows': (ctypes.c_int, [_c_p, _c_p, _c_i32, _c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p, _c_i64, _c_p]),
 }
 
 _lib = None

@@ -29,7 +29,7 @@ int sm_count() {
 
 // implemented in the kernel translation units
 int csr_gather_reduce(const int32_t*, const int32_t*, const float*, const float*, int64_t, int32_t, int32_t, int32_t,
-                      float*, void*, int32_t, float*, cudaStream_t);
+                      float*, void*, int32_t, float*, float*, float*, cudaStream_t);
 int split_rows(const float*, int64_t, int32_t, int32_t, float*, void*, int32_t, float*, cudaStream_t);
 int csr_project_biases(const int32_t*, const int32_t*, const float*, const float*, int64_t, float*, cudaStream_t);
 int pack_item_meta(const float*, const float*, int64_t, float*, int64_t, cudaStream_t);
@@ -40,21 +40,27 @@ size_t rank_full_workspace_bytes(int64_t, int64_t);
 int rank_full(const float*, int32_t*, int64_t, int64_t, void*, size_t, cudaStream_t);
 int score_topk_max_k(int32_t);
 int score_topk_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
-                     int32_t, int32_t, int32_t, float*, int32_t*, cudaStream_t);
+                     int32_t, int32_t, int32_t, float*, int32_t*, const int32_t*, cudaStream_t);
 int score_dense_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
                       float*, int64_t, cudaStream_t);
-int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t, float*, int32_t*, cudaStream_t);
+int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t, int64_t, int64_t, float*, int32_t*,
+               int64_t, const int32_t*, cudaStream_t);
 int score_filter_max_k();
 int score_filter_list_width();
 int operand_stats(const void*, const float*, int64_t, int32_t, float*, float*, cudaStream_t);
 int rescale_hi_global(const void*, const float*, const float*, const int32_t*, int64_t, int32_t, void*, cudaStream_t);
-int pack_item_bias(const float*, const int32_t*, int64_t, float*, int64_t, float*, float*, cudaStream_t);
+int pack_item_bias(const float*, const int32_t*, int64_t, float*, int64_t, float*, float*, float*, cudaStream_t);
 int score_filter_f16(const void*, const float*, const float*, const float*, const void*, const float*, const float*,
-                     const float*, const int32_t*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, float*, int32_t*,
-                     float*, int32_t*, cudaStream_t);
-int rescore_topk(const float*, const float*, const float*, const float*, const int32_t*, const float*, const int32_t*,
-                 const float*, const float*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, int32_t, float*,
-                 int32_t*, int32_t*, cudaStream_t);
+                     const float*, const float*, const int32_t*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t,
+                     float*, int32_t*, float*, cudaStream_t);
+int rescore_topk(const void*, const float*, const void*, const float*, const float*, const float*, const int32_t*,
+                 const float*, const float*, const float*, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, int32_t,
+                 float*, int32_t*, int64_t, int32_t*, cudaStream_t);
+int select_flagged_rows(const int32_t*, int64_t, int32_t*, int32_t, int32_t*, cudaStream_t);
+int gather_operand_rows(const int32_t*, const int32_t*, int32_t, const void*, const float*, const float*, int32_t, void*,
+                        float*, float*, cudaStream_t);
+int scatter_topk_rows(const int32_t*, const int32_t*, int32_t, const float*, const int32_t*, int64_t, int32_t, float*,
+                      int32_t*, int64_t, cudaStream_t);
 
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -62,15 +68,16 @@ static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>
 
 extern "C" {
 
-int trk_version(void) { return 1000; }
+int trk_version(void) { return 2000; }
 
 const char* trk_last_error(void) { return trk::g_last_error; }
 
 int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const float* val, const float* weights,
                               int64_t rows, int32_t n_features, int32_t d, int32_t n_normalize, float* out_f32,
-                              void* out_split, int32_t d_pad, float* out_scale, void* stream) {
+                              void* out_split, int32_t d_pad, float* out_scale, float* out_norm, float* stats,
+                              void* stream) {
   return trk::csr_gather_reduce(indptr, col, val, weights, rows, n_features, d, n_normalize, out_f32, out_split,
-                                d_pad, out_scale, trk::as_stream(stream));
+                                d_pad, out_scale, out_norm, stats, trk::as_stream(stream));
 }
 
 int trk_split_f32_to_f16x2(const float* repr, int64_t rows, int32_t d, int32_t n_normalize, void* out_split,
@@ -122,9 +129,9 @@ int trk_pack_item_meta(const float* item_scale, const float* item_bias, int64_t 
 int trk_score_topk_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
                          const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
                          int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset, float* cand_score,
-                         int32_t* cand_item, void* stream) {
+                         int32_t* cand_item, const int32_t* n_users_live, void* stream) {
   return trk::score_topk_f16x3(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, k,
-                               n_splits, item_id_offset, cand_score, cand_item, trk::as_stream(stream));
+                               n_splits, item_id_offset, cand_score, cand_item, n_users_live, trk::as_stream(stream));
 }
 
 int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
@@ -135,9 +142,10 @@ int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const
 }
 
 int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
-                   int32_t k_in, int32_t k_out, float* out_score, int32_t* out_item, void* stream) {
-  return trk::topk_merge(cand_score, cand_item, n_users, n_lists, k_in, k_out, out_score, out_item,
-                         trk::as_stream(stream));
+                   int32_t k_in, int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score,
+                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, void* stream) {
+  return trk::topk_merge(cand_score, cand_item, n_users, n_lists, k_in, k_out, user_stride, list_stride, out_score,
+                         out_item, out_row_stride, n_users_live, trk::as_stream(stream));
 }
 
 int trk_score_filter_max_k(void) { return trk::score_filter_max_k(); }
@@ -155,29 +163,50 @@ int trk_rescale_hi_global(const void* split, const float* scale, const float* st
 }
 
 int trk_pack_item_bias(const float* item_bias, const int32_t* perm, int64_t n_items, float* out,
-                       int64_t n_items_padded, float* stats, float* block_max, void* stream) {
-  return trk::pack_item_bias(item_bias, perm, n_items, out, n_items_padded, stats, block_max, trk::as_stream(stream));
+                       int64_t n_items_padded, float* stats, float* block_max, float* block_min, void* stream) {
+  return trk::pack_item_bias(item_bias, perm, n_items, out, n_items_padded, stats, block_max, block_min,
+                             trk::as_stream(stream));
 }
 
 int trk_score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                          const float* user_norm, const void* item_hi_global, const float* item_stats,
-                         const float* item_bias_padded, const float* block_bias_max, const int32_t* item_perm,
-                         int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
-                         int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
-                         int32_t* row_flags, void* stream) {
+                         const float* item_bias_padded, const float* block_bias_max, const float* block_bias_min,
+                         const int32_t* item_perm, int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k,
+                         int32_t n_splits, int32_t item_id_offset, float* cand_score, int32_t* cand_item,
+                         float* row_theta, void* stream) {
   return trk::score_filter_f16(user_split, user_scale, user_bias, user_norm, item_hi_global, item_stats,
-                               item_bias_padded, block_bias_max, item_perm, n_users, n_items, d_pad, k, n_splits,
-                               item_id_offset, cand_score, cand_item, row_theta, row_flags, trk::as_stream(stream));
+                               item_bias_padded, block_bias_max, block_bias_min, item_perm, n_users, n_items, d_pad, k,
+                               n_splits, item_id_offset, cand_score, cand_item, row_theta, trk::as_stream(stream));
 }
 
-int trk_rescore_topk_f32(const float* user_repr, const float* item_repr, const float* user_bias,
-                         const float* item_bias, const int32_t* cand_item, const float* row_theta,
-                         const int32_t* row_flags, const float* user_norm, const float* item_stats, int64_t n_users,
-                         int64_t n_items_local, int32_t d, int32_t n_lists, int32_t list_width, int32_t k,
-                         int32_t item_id_offset, float* out_score, int32_t* out_item, int32_t* out_flag, void* stream) {
-  return trk::rescore_topk(user_repr, item_repr, user_bias, item_bias, cand_item, row_theta, row_flags, user_norm,
-                           item_stats, n_users, n_items_local, d, n_lists, list_width, k, item_id_offset, out_score,
-                           out_item, out_flag, trk::as_stream(stream));
+int trk_rescore_topk_split(const void* user_split, const float* user_scale, const void* item_split,
+                           const float* item_scale, const float* user_bias, const float* item_bias,
+                           const int32_t* cand_item, const float* row_theta, const float* user_norm,
+                           const float* item_stats, int64_t n_users, int64_t n_items_local, int32_t d_pad,
+                           int32_t n_lists, int32_t list_width, int32_t k, int32_t item_id_offset, float* out_score,
+                           int32_t* out_item, int64_t out_row_stride, int32_t* out_flag, void* stream) {
+  return trk::rescore_topk(user_split, user_scale, item_split, item_scale, user_bias, item_bias, cand_item, row_theta,
+                           user_norm, item_stats, n_users, n_items_local, d_pad, n_lists, list_width, k, item_id_offset,
+                           out_score, out_item, out_row_stride, out_flag, trk::as_stream(stream));
+}
+
+int trk_select_flagged_rows(const int32_t* flags, int64_t n, int32_t* idx, int32_t capacity, int32_t* counters,
+                            void* stream) {
+  return trk::select_flagged_rows(flags, n, idx, capacity, counters, trk::as_stream(stream));
+}
+
+int trk_gather_operand_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const void* split,
+                            const float* scale, const float* bias, int32_t d_pad, void* sub_split, float* sub_scale,
+                            float* sub_bias, void* stream) {
+  return trk::gather_operand_rows(idx, counters, capacity, split, scale, bias, d_pad, sub_split, sub_scale, sub_bias,
+                                  trk::as_stream(stream));
+}
+
+int trk_scatter_topk_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const float* sub_score,
+                          const int32_t* sub_item, int64_t sub_row_stride, int32_t k, float* out_score,
+                          int32_t* out_item, int64_t out_row_stride, void* stream) {
+  return trk::scatter_topk_rows(idx, counters, capacity, sub_score, sub_item, sub_row_stride, k, out_score, out_item,
+                                out_row_stride, trk::as_stream(stream));
 }
 
 }  // extern "C"

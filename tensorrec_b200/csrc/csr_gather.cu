@@ -80,11 +80,19 @@ __device__ __forceinline__ void split_f16(float x, float up, __half* hi, __half*
 
 // Row epilogue shared by the gather kernel and the dense->split converter.
 // VEC: every lane owns CH float4 chunks, chunk index = lane + G*j ; scalar: CH floats, element = lane + G*j.
+// Running maxima a thread carries over all the rows it finishes (reduced once per warp at the end of the kernel: one
+// atomic per row would serialise a million updates of one address in L2).
+struct RowStats {
+  float max_norm = 0.0f;    // largest row norm (upper bound, see below)
+  float max_scale = 0.0f;   // largest 2^-e among the non-zero rows == the scale of the row with the largest element
+};
+
 template <int G, int CH, bool VEC>
 __device__ __forceinline__ void row_epilogue(float (&acc)[CH][VEC ? 4 : 1], int lane, int64_t row, bool active,
                                              int d, int n_normalize, float* __restrict__ out_f32,
                                              __half* __restrict__ out_split, int d_pad,
-                                             float* __restrict__ out_scale) {
+                                             float* __restrict__ out_scale, float* __restrict__ out_norm = nullptr,
+                                             RowStats* st = nullptr) {
   constexpr int W = VEC ? 4 : 1;
   for (int n = 0; n < n_normalize; ++n) {
     float ss = 0.0f;
@@ -100,6 +108,21 @@ __device__ __forceinline__ void row_epilogue(float (&acc)[CH][VEC ? 4 : 1], int 
       for (int w = 0; w < W; ++w) acc[j][w] *= inv_norm;
   }
   // (the shuffles above are executed by every lane of the warp; only stores are predicated on `active`)
+  float row_ss = 0.0f;
+  if (out_norm != nullptr || st != nullptr) {
+    // |row|_2 as an UPPER bound (the filter's error bound is proportional to it): inflated by 2^-9, which covers the
+    // rounding of this reduction and of the 22-bit split operand
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int w = 0; w < W; ++w) row_ss = fmaf(acc[j][w], acc[j][w], row_ss);
+    row_ss = group_sum<G>(row_ss);
+    const float norm = sqrtf(row_ss) * 1.002f;
+    if (active && lane == 0) {
+      if (out_norm != nullptr) out_norm[row] = norm;
+      if (st != nullptr) st->max_norm = fmaxf(st->max_norm, norm);
+    }
+  }
   if (out_f32 != nullptr && active) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -123,7 +146,10 @@ __device__ __forceinline__ void row_epilogue(float (&acc)[CH][VEC ? 4 : 1], int 
     float inv;
     const float up = row_scale_pow2(m, &inv);
     if (!active) return;
-    if (lane == 0) out_scale[row] = inv;
+    if (lane == 0) {
+      out_scale[row] = inv;
+      if (st != nullptr && m > 0.0f) st->max_scale = fmaxf(st->max_scale, inv);   // all-zero rows carry the neutral 1
+    }
     __half* hi_row = out_split + row * (2 * static_cast<int64_t>(d_pad));
     __half* lo_row = hi_row + d_pad;
 #pragma unroll
@@ -152,7 +178,7 @@ __global__ void __launch_bounds__(kGatherThreads, 4)
 csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
                          const float* __restrict__ val, const float* __restrict__ weights, int64_t rows, int d,
                          int n_normalize, float* __restrict__ out_f32, __half* __restrict__ out_split, int d_pad,
-                         float* __restrict__ out_scale) {
+                         float* __restrict__ out_scale, float* __restrict__ out_norm, float* __restrict__ stats) {
   constexpr int W = VEC ? 4 : 1;
   constexpr int kGroups = kGatherThreads / G;
   __shared__ int32_t s_ptr[kTileRows + 1];
@@ -163,6 +189,7 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
   const int group = tid / G;
   const int lane = tid % G;
   const int64_t n_tiles = ceil_div(rows, kTileRows);
+  RowStats st;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = tile * kTileRows;
@@ -244,9 +271,23 @@ csr_gather_reduce_kernel(const int32_t* __restrict__ indptr, const int32_t* __re
               for (int w = 0; w < W; ++w) acc[j][w] = fmaf(v[q], wv[q][j][w], acc[j][w]);
           }
       }
-      row_epilogue<G, CH, VEC>(acc, lane, r0 + rr, active, d, n_normalize, out_f32, out_split, d_pad, out_scale);
+      row_epilogue<G, CH, VEC>(acc, lane, r0 + rr, active, d, n_normalize, out_f32, out_split, d_pad, out_scale,
+                               out_norm, stats != nullptr ? &st : nullptr);
     }
     __syncthreads();  // the next tile overwrites the staging buffers
+  }
+  if (stats != nullptr) {
+    // non-negative floats order like their bit patterns: atomicMax on the bits is order independent -> deterministic
+    float mn = st.max_norm, ms = st.max_scale;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+    }
+    if (tid % 32 == 0) {
+      atomicMax(reinterpret_cast<int*>(stats + 0), __float_as_int(mn));
+      atomicMax(reinterpret_cast<int*>(stats + 1), __float_as_int(ms));
+    }
   }
 }
 
@@ -400,7 +441,8 @@ int gather_grid(int64_t n_tiles) {
 
 int csr_gather_reduce(const int32_t* indptr, const int32_t* col, const float* val, const float* weights,
                       int64_t rows, int32_t n_features, int32_t d, int32_t n_normalize, float* out_f32,
-                      void* out_split, int32_t d_pad, float* out_scale, cudaStream_t stream) {
+                      void* out_split, int32_t d_pad, float* out_scale, float* out_norm, float* stats,
+                      cudaStream_t stream) {
   TRK_CHECK_ARG(indptr && weights, "csr_gather_reduce: null indptr/weights");
   TRK_CHECK_ARG(rows >= 0 && d >= 1 && n_features >= 0, "csr_gather_reduce: bad sizes rows=%lld d=%d",
                 static_cast<long long>(rows), d);
@@ -411,6 +453,7 @@ int csr_gather_reduce(const int32_t* indptr, const int32_t* col, const float* va
     TRK_CHECK_ARG(d_pad >= d && d_pad % 64 == 0, "csr_gather_reduce: d_pad=%d must be a multiple of 64 >= d=%d",
                   d_pad, d);
   }
+  if (stats != nullptr) TRK_CHECK_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(float), stream));
   if (rows == 0) return TRK_OK;
   const bool aligned = (reinterpret_cast<uintptr_t>(weights) % 16 == 0) &&
                        (out_f32 == nullptr || reinterpret_cast<uintptr_t>(out_f32) % 16 == 0) &&
@@ -423,7 +466,8 @@ int csr_gather_reduce(const int32_t* indptr, const int32_t* col, const float* va
   const int grid = gather_grid(ceil_div(rows, kTileRows));
 #define CALL(G, CH, VEC)                                                                                     \
   csr_gather_reduce_kernel<G, CH, VEC><<<grid, kGatherThreads, 0, stream>>>(                                 \
-      indptr, col, val, weights, rows, d, n_normalize, out_f32, static_cast<__half*>(out_split), d_pad, out_scale)
+      indptr, col, val, weights, rows, d, n_normalize, out_f32, static_cast<__half*>(out_split), d_pad, out_scale, \
+      out_norm, stats)
   TRK_DISPATCH_ROWSHAPE(s, CALL);
 #undef CALL
   TRK_CHECK_LAUNCH();

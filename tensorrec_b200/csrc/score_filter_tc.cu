@@ -61,6 +61,7 @@ struct FilterParams {
   const float* user_norm;      // |u|_2 per user
   const float* item_bias;      // [padded items] in PROCESSING order (see item_perm), padding = -inf
   const float* block_bias_max; // max item bias of every block of 128 processing positions (-inf for all-padding)
+  const float* block_bias_min; // min item bias of every block (-inf as soon as the block holds padding); may be null
   const int32_t* item_perm;    // processing position -> local item index (items sorted by bias), or null = identity
   const float* item_stats;     // device: [0] = max_j |i_j|_2, [1] = global item scale (2^-E), [2] = max_j |bias_j|
   int64_t n_users;
@@ -78,8 +79,7 @@ struct FilterParams {
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
   float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, kKeepMax] global ids (sentinel INT32_MAX)
-  float* row_theta;            // [n_users, n_splits] final admission threshold
-  int32_t* row_flags;          // [n_users, n_splits] reserved (0); certification happens in rescore_topk_kernel
+  float* row_theta;            // [n_users, n_splits] final admission threshold (certified by rescore_topk_kernel)
 };
 
 struct FilterLayout {
@@ -258,6 +258,40 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
              buf_row_addr, cnt, n_res, lane, k);
     admit_16(acc + 16, a1 + bmax_scaled > tau, pos_base + 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max,
              m3, buf_row_addr, cnt, n_res, lane, k);
+  }
+}
+
+// ---- first tile of a work unit: a threshold to start from -----------------------------------------------------------
+// With tau = -inf every column of the first tile is admitted: 128 appends and 8 warp-cooperative compactions per row,
+// 32 rows of a warp one after the other (~50 us per 256-user unit; 2 % of a 1M-item sweep but 15 % of a 125K-item
+// shard, which is what held the 8-GPU run at 0.74 of the tensor peak per shard).  Instead every thread first reduces
+// its row of the first accumulator to 16 group maxima (8 columns each), sorts them in registers and takes the k-th
+// largest, A: k DIFFERENT columns have acc >= A, their biases are >= the block minimum, so the k-th best approximate
+// score of the tile is >= fma(A, c, ub) + bmin and theta may start 2.25 m below that.  The tile is then filtered as
+// usual: ~1.5 k admissions per row instead of 128, no compaction.
+__device__ __forceinline__ float acc_max_8(const uint32_t* acc) {
+  return fmaxf(fmaxf(fmaxf(__uint_as_float(acc[0]), __uint_as_float(acc[1])),
+                     fmaxf(__uint_as_float(acc[2]), __uint_as_float(acc[3]))),
+               fmaxf(fmaxf(__uint_as_float(acc[4]), __uint_as_float(acc[5])),
+                     fmaxf(__uint_as_float(acc[6]), __uint_as_float(acc[7]))));
+}
+// bitonic network on 16 registers, descending; every index is a compile-time constant after unrolling
+__device__ __forceinline__ void sort16_desc(float (&g)[16]) {
+#pragma unroll
+  for (int size = 2; size <= 16; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const float hi = fmaxf(g[i], g[j]), lo = fminf(g[i], g[j]);
+          g[i] = desc ? hi : lo;
+          g[j] = desc ? lo : hi;
+        }
+      }
+    }
   }
 }
 
@@ -485,6 +519,38 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tcgen05_fence_after();
         const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
+        if (t == t0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
+          const float bmin = __ldg(p.block_bias_min + t0);   // the same for the whole CTA: warp-uniform branch
+          if (bmin > kNegInf) {
+            float g[16];
+            tmem_ld_32x32b_x32(taddr, ra);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 32, rb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[q] = acc_max_8(ra + 8 * q);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 64, ra);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[4 + q] = acc_max_8(rb + 8 * q);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 96, rb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[8 + q] = acc_max_8(ra + 8 * q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g[12 + q] = acc_max_8(rb + 8 * q);
+            sort16_desc(g);
+            float a_k = g[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) a_k = (i < p.k) ? g[i] : a_k;   // g[k - 1]: the k-th largest group maximum
+            const float th0 = (fmaf(a_k, c, ubias) + bmin) - m3;
+            if (th0 == th0) {   // not NaN (infinite biases / margins): otherwise the sweep starts from -inf as before
+              theta = th0;
+              const float tt = (theta - ubias) * inv_c;
+              tau = tt - 8.0f * 1.1920929e-7f * fabsf(tt) - 1e-30f;
+            }
+          }
+        }
         if (p.debug_mode == 2 || p.debug_mode == 6) goto drained;
         if (p.debug_mode == 1) {
           float acc_dbg = 0.0f;
@@ -538,8 +604,10 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
           os[e] = s;
           oi[e] = id;
         }
-        p.row_theta[base] = fmaxf(theta, drop_max);   // every excluded item has an approximate score <= this
-        p.row_flags[base] = 0;
+        // every excluded item has an approximate score <= this; a NaN (inf - inf with infinite biases) must not read
+        // as "nothing was excluded": +inf makes the certificate fail and the row goes through the exact kernel
+        const bool th_nan = theta != theta || drop_max != drop_max;
+        p.row_theta[base] = th_nan ? __int_as_float(0x7f800000) : fmaxf(theta, drop_max);
       }
       __syncwarp();
     }
@@ -701,13 +769,13 @@ int rescale_hi_global(const void* split, const float* scale, const float* stats,
 
 int score_filter_f16(const void* user_split, const float* user_scale, const float* user_bias,
                      const float* user_norm, const void* item_hi, const float* item_stats, const float* item_bias,
-                     const float* block_bias_max, const int32_t* item_perm, int64_t n_users, int64_t n_items,
-                     int32_t d_pad, int32_t k, int32_t n_splits,
+                     const float* block_bias_max, const float* block_bias_min, const int32_t* item_perm,
+                     int64_t n_users, int64_t n_items, int32_t d_pad, int32_t k, int32_t n_splits,
                      int32_t item_id_offset, float* cand_score, int32_t* cand_item, float* row_theta,
-                     int32_t* row_flags, cudaStream_t stream) {
+                     cudaStream_t stream) {
   TRK_CHECK_ARG(user_split && user_scale && user_norm && item_hi && item_stats && item_bias && block_bias_max,
                 "score_filter: null input");
-  TRK_CHECK_ARG(cand_score && cand_item && row_theta && row_flags, "score_filter: null output");
+  TRK_CHECK_ARG(cand_score && cand_item && row_theta, "score_filter: null output");
   TRK_CHECK_ARG(n_users >= 1 && n_items >= 1 && n_splits >= 1, "score_filter: empty shape");
   TRK_CHECK_ARG(n_users < (1ll << 31) && n_items < (1ll << 31) - 512, "score_filter: shape exceeds int32 indexing");
   if (d_pad != 64 && d_pad != 128) {
@@ -730,6 +798,7 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.user_norm = user_norm;
   p.item_bias = item_bias;
   p.block_bias_max = block_bias_max;
+  p.block_bias_min = getenv("TRK_FILTER_NO_WARMSTART") != nullptr ? nullptr : block_bias_min;
   p.item_perm = item_perm;
   p.item_stats = item_stats;
   p.n_users = n_users;
@@ -744,7 +813,6 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.cand_score = cand_score;
   p.cand_item = cand_item;
   p.row_theta = row_theta;
-  p.row_flags = row_flags;
   {
     const char* dbg = getenv("TRK_FILTER_DEBUG");
     p.debug_mode = dbg != nullptr ? atoi(dbg) : 0;

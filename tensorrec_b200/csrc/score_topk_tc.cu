@@ -57,6 +57,8 @@ struct TcParams {
   float* dense_out;         // dense mode output
   int64_t dense_stride;
   int32_t tma_store;        // dense mode: 1 = rows are 16-byte aligned, the epilogue stores through TMA
+  const int32_t* n_users_live;  // device, may be null: only the first *n_users_live user rows hold work (rows flagged
+                                // by the filter's certificate, counted on the device) -- later user blocks are skipped
 };
 
 // shared-memory carve-up (offsets from a 1024-byte aligned base)
@@ -199,6 +201,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   const int lane = threadIdx.x % 32;
   constexpr int n_kb2 = 2 * kNKB;
   const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * p.n_splits;
+  // user blocks at or beyond this one hold no rows (every role skips them: the same test in all three loops)
+  const int live_blocks = p.n_users_live != nullptr
+                              ? static_cast<int>(min(static_cast<int64_t>(p.n_user_blocks),
+                                                     ceil_div(static_cast<int64_t>(__ldg(p.n_users_live)), kBlockM)))
+                              : p.n_user_blocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_users);
@@ -237,7 +244,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         const int sp = static_cast<int>(w / p.n_user_blocks);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        if (t1 <= t0) continue;
+        if (t1 <= t0 || ub >= live_blocks) continue;
         mbar_wait(a_empty, (witer & 1) ^ 1);  // the MMAs of the previous work item no longer read A
         if (elect_one()) {
           mbar_arrive_expect_tx(a_full, n_kb2 * kATileBytes);
@@ -289,7 +296,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
         const int sp = static_cast<int>(w / p.n_user_blocks);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        if (t1 <= t0) continue;
+        if (t1 <= t0 || static_cast<int>(w % p.n_user_blocks) >= live_blocks) continue;
         mbar_wait(a_full, witer & 1);
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
@@ -353,6 +360,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
       const int sp = static_cast<int>(w / p.n_user_blocks);
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      if (ub >= live_blocks) continue;
       const int64_t u = static_cast<int64_t>(ub) * kBlockM + row;
       const bool u_ok = u < p.n_users;
       const float su = u_ok ? __ldg(p.user_scale + u) : 0.0f;
@@ -507,7 +515,8 @@ template <bool kDense>
 static int launch_tc(const void* user_split, const float* user_scale, const float* user_bias,
                      const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
                      int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset, float* cand_score,
-                     int32_t* cand_item, float* dense_out, int64_t dense_stride, cudaStream_t stream) {
+                     int32_t* cand_item, float* dense_out, int64_t dense_stride, const int32_t* n_users_live,
+                     cudaStream_t stream) {
   TRK_CHECK_ARG(user_split && user_scale && item_split && item_meta, "score_tc: null operand");
   TRK_CHECK_ARG(n_users >= 1 && n_items >= 1, "score_tc: empty shape");
   TRK_CHECK_ARG(n_users < (1ll << 31) && n_items < (1ll << 31) - 512, "score_tc: shape exceeds int32 indexing");
@@ -546,6 +555,7 @@ static int launch_tc(const void* user_split, const float* user_scale, const floa
   p.cand_item = cand_item;
   p.dense_out = dense_out;
   p.dense_stride = dense_stride;
+  p.n_users_live = n_users_live;
   p.tma_store = (kDense && dense_stride % 4 == 0 && reinterpret_cast<uintptr_t>(dense_out) % 16 == 0) ? 1 : 0;
   p.n_stages = pick_stages(p.n_kblocks, p.k, p.tma_store != 0);
   TRK_CHECK_ARG(p.n_stages >= 2, "score_tc: shared memory budget exceeded (d_pad=%d k=%d)", d_pad, k);
@@ -584,9 +594,9 @@ static int launch_tc(const void* user_split, const float* user_scale, const floa
 int score_topk_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
                      const void* item_split, const float* item_meta, int64_t n_users, int64_t n_items,
                      int32_t d_pad, int32_t k, int32_t n_splits, int32_t item_id_offset, float* cand_score,
-                     int32_t* cand_item, cudaStream_t stream) {
+                     int32_t* cand_item, const int32_t* n_users_live, cudaStream_t stream) {
   return launch_tc<false>(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, k,
-                          n_splits, item_id_offset, cand_score, cand_item, nullptr, 0, stream);
+                          n_splits, item_id_offset, cand_score, cand_item, nullptr, 0, n_users_live, stream);
 }
 
 int score_dense_f16x3(const void* user_split, const float* user_scale, const float* user_bias,
@@ -599,7 +609,7 @@ int score_dense_f16x3(const void* user_split, const float* user_scale, const flo
   if (splits > n_tiles) splits = n_tiles;
   if (splits < 1) splits = 1;
   return launch_tc<true>(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, 0,
-                         static_cast<int32_t>(splits), 0, nullptr, nullptr, out, out_row_stride, stream);
+                         static_cast<int32_t>(splits), 0, nullptr, nullptr, out, out_row_stride, nullptr, stream);
 }
 
 }  // namespace trk

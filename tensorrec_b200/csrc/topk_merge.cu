@@ -1,7 +1,8 @@
 // Merge of per-(user, list) top-k candidate lists into the global per-user top-k.
 //
-// Lists come from the n_splits item ranges of one GPU and/or from the item shards of the other GPUs (gathered by
-// one NCCL all-gather in the host layer).  Every list is ordered by (score descending, item id ascending) -- the
+// Lists come from the n_splits item ranges of one GPU and/or from the item shards of the other GPUs (exchanged by
+// one NCCL all-to-all in the host layer: list l of user u sits at cand + u * user_stride + l * list_stride, which
+// covers both the [U, L, k] layout of one GPU and the [L, U_slice, 2k] receive buffer of the exchange).  Every list is ordered by (score descending, item id ascending) -- the
 // order tf.nn.top_k gives the reference (tensorrec/recommendation_graphs.py:81) -- and padded with
 // (-inf, INT32_MAX).  One warp per user performs an n_lists-way merge: lane l holds the heads of lists l, l+32, ...;
 // each of the k_out rounds is a warp arg-best over the heads.  Integer/float compares only: deterministic.
@@ -17,14 +18,17 @@ __device__ __forceinline__ bool cand_better(float s, int32_t i, float bs, int32_
 
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_item, int64_t n_users,
-                  int n_lists, int k_in, int k_out, float* __restrict__ out_score, int32_t* __restrict__ out_item) {
+                  int n_lists, int k_in, int k_out, int64_t user_stride, int64_t list_stride,
+                  float* __restrict__ out_score, int32_t* __restrict__ out_item, int64_t out_stride,
+                  const int32_t* __restrict__ n_users_live) {
+  if (n_users_live != nullptr) n_users = min(n_users, static_cast<int64_t>(*n_users_live));
   const int lane = threadIdx.x % 32;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * blockDim.x / 32;
   const float kNegInf = -__int_as_float(0x7f800000);
   for (int64_t u = warp; u < n_users; u += n_warps) {
-    const float* cs = cand_score + u * n_lists * k_in;
-    const int32_t* ci = cand_item + u * n_lists * k_in;
+    const float* cs = cand_score + u * user_stride;
+    const int32_t* ci = cand_item + u * user_stride;
     int pos[kMergeMaxListsPerLane];
 #pragma unroll
     for (int j = 0; j < kMergeMaxListsPerLane; ++j) pos[j] = 0;
@@ -36,8 +40,8 @@ topk_merge_kernel(const float* __restrict__ cand_score, const int32_t* __restric
       for (int j = 0; j < kMergeMaxListsPerLane; ++j) {
         const int l = lane + 32 * j;
         if (l < n_lists && pos[j] < k_in) {
-          const float s = cs[l * k_in + pos[j]];
-          const int32_t i = ci[l * k_in + pos[j]];
+          const float s = cs[l * list_stride + pos[j]];
+          const int32_t i = ci[l * list_stride + pos[j]];
           if (cand_better(s, i, bs, bi)) {
             bs = s;
             bi = i;
@@ -63,17 +67,19 @@ topk_merge_kernel(const float* __restrict__ cand_score, const int32_t* __restric
           if (j == bj) pos[j] += 1;
       }
       if (lane == 0) {
-        out_score[u * k_out + round] = ws;
-        out_item[u * k_out + round] = wi;
+        out_score[u * out_stride + round] = ws;
+        out_item[u * out_stride + round] = wi;
       }
     }
   }
 }
 
 int topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists, int32_t k_in,
-               int32_t k_out, float* out_score, int32_t* out_item, cudaStream_t stream) {
+               int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score, int32_t* out_item,
+               int64_t out_row_stride, const int32_t* n_users_live, cudaStream_t stream) {
   TRK_CHECK_ARG(cand_score && cand_item && out_score && out_item, "topk_merge: null pointer");
   TRK_CHECK_ARG(n_users >= 0 && n_lists >= 1 && k_in >= 1 && k_out >= 1, "topk_merge: bad sizes");
+  TRK_CHECK_ARG(user_stride >= 1 && list_stride >= 1 && out_row_stride >= k_out, "topk_merge: bad strides");
   TRK_CHECK_ARG(n_lists <= 32 * kMergeMaxListsPerLane, "topk_merge: n_lists=%d exceeds %d", n_lists,
                 32 * kMergeMaxListsPerLane);
   if (n_users == 0) return TRK_OK;
@@ -81,7 +87,8 @@ int topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_user
   const int64_t blocks = ceil_div(n_users, threads / 32);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   topk_merge_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
-      cand_score, cand_item, n_users, n_lists, k_in, k_out, out_score, out_item);
+      cand_score, cand_item, n_users, n_lists, k_in, k_out, user_stride, list_stride, out_score, out_item,
+      out_row_stride, n_users_live);
   TRK_CHECK_LAUNCH();
   return TRK_OK;
 }

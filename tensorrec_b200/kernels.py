@@ -111,25 +111,63 @@ class DeviceCSR(object):
         return 4 * (self.indptr.numel() + self.col.numel() + self.val.numel())
 
 
-def gather_reduce(csr, weights, n_normalize=0, want_f32=True, split_d_pad=None):
-    """K1.  Returns (repr_f32 or None, split or None, scale or None)."""
+K1_MAX_WIDTH = 512      # widest row one K1 launch covers (256 when the width is not a multiple of 4)
+
+
+def gather_reduce(csr, weights, n_normalize=0, want_f32=True, split_d_pad=None, want_norm=False, stats=None):
+    """K1.  Returns (repr_f32 or None, split or None, scale or None[, norm]).
+
+    want_norm: also return the row norms (upper bounds) formed in K1's epilogue; stats: float32[3] that receives the
+    max norm / max row scale (zeroed by the call).  Both feed the filter form of the fused top-k."""
     lib = require_cuda()
     rows, n_features = csr.shape
     d = int(weights.shape[1])
     if int(weights.shape[0]) != n_features:
         raise ValueError('feature matrix has %d columns but the weights have %d rows' % (n_features, weights.shape[0]))
     dev = weights.device
+    if split_d_pad is None and not want_norm and stats is None and (d > K1_MAX_WIDTH or (d % 4 != 0 and d > 256)):
+        return _gather_reduce_wide(csr, weights, n_normalize), None, None
     out = torch.empty((rows, d), dtype=torch.float32, device=dev) if want_f32 else None
-    split = scale = None
+    split = scale = norm = None
     d_pad = 0
     if split_d_pad is not None:
         d_pad = int(split_d_pad)
         split = torch.empty((rows, 2 * d_pad), dtype=torch.float16, device=dev)
         scale = torch.empty((rows,), dtype=torch.float32, device=dev)
+    if want_norm:
+        norm = torch.empty((rows,), dtype=torch.float32, device=dev)
     rc = lib.trk_csr_gather_reduce_f32(_p(csr.indptr), _p(csr.col), _p(csr.val), _p(weights), rows, n_features, d,
-                                       int(n_normalize), _p(out), _p(split), d_pad, _p(scale), _stream())
+                                       int(n_normalize), _p(out), _p(split), d_pad, _p(scale), _p(norm), _p(stats),
+                                       _stream())
     _lib.check(rc, 'trk_csr_gather_reduce_f32')
+    if want_norm:
+        return out, split, scale, norm
     return out, split, scale
+
+
+def _gather_reduce_wide(csr, weights, n_normalize):
+    """Rows wider than one K1 launch covers (n_components > 512, e.g. the 4 x n_components hidden layer of a
+    ReLURepresentationGraph): the component axis is cut into column blocks of at most 512, one K1 launch each (every
+    output element is still the same fp32 FMA chain in CSR order), normalisation afterwards over the whole row."""
+    rows = csr.shape[0]
+    d = int(weights.shape[1])
+    out = torch.empty((rows, d), dtype=torch.float32, device=weights.device)
+    step = K1_MAX_WIDTH
+    for c0 in range(0, d, step):
+        c1 = min(d, c0 + step)
+        block, _, _ = gather_reduce(csr, weights[:, c0:c1].contiguous(), want_f32=True)
+        out[:, c0:c1] = block
+    for _ in range(int(n_normalize)):
+        _l2_normalize_rows_any_width_(out)
+    return out
+
+
+def _l2_normalize_rows_any_width_(x):
+    if x.shape[1] <= 1024:
+        return l2_normalize_rows_(x)
+    # tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12)); rows this wide are outside every kernel's row shape
+    x.mul_(torch.rsqrt(torch.clamp((x * x).sum(dim=1, keepdim=True), min=1e-12)))
+    return x
 
 
 def split_f32(repr_f32, n_normalize=0, d_pad=None):
@@ -233,8 +271,9 @@ def default_splits(n_users, n_items):
 
 
 def score_topk(user_split, user_scale, user_bias, item_split, item_meta, n_users, n_items, d_pad, k, n_splits=None,
-               item_id_offset=0):
-    """K2+K3 fused.  Returns (cand_score [U, n_splits, k] f32, cand_item [U, n_splits, k] i32)."""
+               item_id_offset=0, n_users_live=None):
+    """K2+K3 fused.  Returns (cand_score [U, n_splits, k] f32, cand_item [U, n_splits, k] i32).
+    n_users_live: device int32 tensor; only its first element's worth of user rows is processed."""
     lib = require_cuda()
     if n_splits is None:
         n_splits = default_splits(n_users, n_items)
@@ -243,7 +282,7 @@ def score_topk(user_split, user_scale, user_bias, item_split, item_meta, n_users
     cand_item = torch.empty((n_users, n_splits, k), dtype=torch.int32, device=dev)
     rc = lib.trk_score_topk_f16x3(_p(user_split), _p(user_scale), _p(user_bias), _p(item_split), _p(item_meta),
                                   n_users, n_items, int(d_pad), int(k), int(n_splits), int(item_id_offset),
-                                  _p(cand_score), _p(cand_item), _stream())
+                                  _p(cand_score), _p(cand_item), _p(n_users_live), _stream())
     _lib.check(rc, 'trk_score_topk_f16x3')
     return cand_score, cand_item
 
@@ -258,16 +297,58 @@ def score_dense_tc(user_split, user_scale, user_bias, item_split, item_meta, n_u
     return out
 
 
-def topk_merge(cand_score, cand_item, k_out):
-    """[U, L, k_in] candidate lists -> ([U, k_out] scores, [U, k_out] item ids)."""
+class PackedTopK(object):
+    """Top-k result of a batch of users in the layout the multi-GPU exchange sends: int32 [n_users, 2k], row u =
+    k scores (float32 bits) then k item ids.  `scores` / `items` are views."""
+
+    def __init__(self, n_users, k, device, buf=None):
+        self.k = int(k)
+        self.buf = torch.empty((int(n_users), 2 * self.k), dtype=torch.int32, device=device) if buf is None else buf
+
+    @property
+    def n_users(self):
+        return int(self.buf.shape[0])
+
+    @property
+    def scores(self):
+        return self.buf[:, :self.k].view(torch.float32)
+
+    @property
+    def items(self):
+        return self.buf[:, self.k:]
+
+    def score_ptr(self):
+        return ctypes.c_void_p(self.buf.data_ptr())
+
+    def item_ptr(self):
+        return ctypes.c_void_p(self.buf.data_ptr() + 4 * self.k)
+
+
+def topk_merge(cand_score, cand_item, k_out, out=None, n_users_live=None):
+    """[U, L, k_in] candidate lists -> PackedTopK [U, k_out] (top scores, top item ids)."""
     lib = require_cuda()
     n_users, n_lists, k_in = cand_score.shape
-    out_s = torch.empty((n_users, k_out), dtype=torch.float32, device=cand_score.device)
-    out_i = torch.empty((n_users, k_out), dtype=torch.int32, device=cand_score.device)
-    rc = lib.trk_topk_merge(_p(cand_score.contiguous()), _p(cand_item.contiguous()), n_users, n_lists, k_in,
-                            int(k_out), _p(out_s), _p(out_i), _stream())
+    cand_score, cand_item = cand_score.contiguous(), cand_item.contiguous()
+    if out is None:
+        out = PackedTopK(n_users, k_out, cand_score.device)
+    rc = lib.trk_topk_merge(_p(cand_score), _p(cand_item), n_users, n_lists, k_in, int(k_out), n_lists * k_in, k_in,
+                            out.score_ptr(), out.item_ptr(), 2 * out.k, _p(n_users_live), _stream())
     _lib.check(rc, 'trk_topk_merge')
-    return out_s, out_i
+    return out
+
+
+def topk_merge_received(recv, n_users, n_lists, k):
+    """Merge of the exchange receive buffer int32 [n_lists, n_users, 2k] (list l = the candidates rank l found for
+    THIS rank's user slice) -> PackedTopK [n_users, k]."""
+    lib = require_cuda()
+    out = PackedTopK(n_users, k, recv.device)
+    if n_users == 0:
+        return out
+    base = recv.data_ptr()
+    rc = lib.trk_topk_merge(ctypes.c_void_p(base), ctypes.c_void_p(base + 4 * k), n_users, int(n_lists), int(k), int(k),
+                            2 * k, n_users * 2 * k, out.score_ptr(), out.item_ptr(), 2 * k, None, _stream())
+    _lib.check(rc, 'trk_topk_merge')
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -301,14 +382,18 @@ def rescale_hi_global(split, scale, stats, d_pad, perm=None):
     return out
 
 
-def pack_item_bias(item_bias, n_items, stats, device, perm=None):
-    """Returns (bias in processing order padded with -inf, max bias per block of 128 positions)."""
+def pack_item_bias(item_bias, n_items, stats, device, perm=None, want_min=False):
+    """Returns (bias in processing order padded with -inf, max bias per block of 128 positions[, min bias per block])."""
     lib = require_cuda()
     n_pad = padded_items(n_items)
     out = torch.empty((n_pad,), dtype=torch.float32, device=device)
     block_max = torch.empty((n_pad // 128,), dtype=torch.float32, device=device)
-    rc = lib.trk_pack_item_bias(_p(item_bias), _p(perm), n_items, _p(out), n_pad, _p(stats), _p(block_max), _stream())
+    block_min = torch.empty((n_pad // 128,), dtype=torch.float32, device=device) if want_min else None
+    rc = lib.trk_pack_item_bias(_p(item_bias), _p(perm), n_items, _p(out), n_pad, _p(stats), _p(block_max),
+                                _p(block_min), _stream())
     _lib.check(rc, 'trk_pack_item_bias')
+    if want_min:
+        return out, block_max, block_min
     return out, block_max
 
 
@@ -321,7 +406,8 @@ def bias_processing_order(item_bias):
 
 
 def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_stats, item_bias_pad, block_bias_max,
-                 item_perm, n_users, n_items, d_pad, k, n_splits=None, item_id_offset=0):
+                 item_perm, n_users, n_items, d_pad, k, n_splits=None, item_id_offset=0, block_bias_min=None):
+    """Filter pass.  Returns (cand_score, cand_item [U, n_splits, 16], theta [U, n_splits])."""
     lib = require_cuda()
     if n_splits is None:
         n_splits = default_splits(n_users, n_items)
@@ -330,31 +416,30 @@ def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_sta
     cand_s = torch.empty((n_users, n_splits, width), dtype=torch.float32, device=dev)
     cand_i = torch.empty((n_users, n_splits, width), dtype=torch.int32, device=dev)
     theta = torch.empty((n_users, n_splits), dtype=torch.float32, device=dev)
-    flags = torch.empty((n_users, n_splits), dtype=torch.int32, device=dev)
     rc = lib.trk_score_filter_f16(_p(user_split), _p(user_scale), _p(user_bias), _p(user_norm), _p(item_hi),
-                                  _p(item_stats), _p(item_bias_pad), _p(block_bias_max), _p(item_perm), n_users,
-                                  n_items, int(d_pad), int(k),
-                                  int(n_splits), int(item_id_offset), _p(cand_s), _p(cand_i), _p(theta), _p(flags),
-                                  _stream())
+                                  _p(item_stats), _p(item_bias_pad), _p(block_bias_max), _p(block_bias_min),
+                                  _p(item_perm), n_users, n_items, int(d_pad), int(k), int(n_splits),
+                                  int(item_id_offset), _p(cand_s), _p(cand_i), _p(theta), _stream())
     _lib.check(rc, 'trk_score_filter_f16')
-    return cand_s, cand_i, theta, flags
+    return cand_s, cand_i, theta
 
 
-def rescore_topk(user_repr, item_repr, user_bias, item_bias, cand_item, theta, flags, user_norm, item_stats, k,
-                 item_id_offset=0):
+def rescore_topk(users, items, cand_item, theta, user_norm, item_stats, k, item_id_offset=0, out=None):
+    """Survivors of the filter -> (PackedTopK [U, k], flags int32 [U]); flags mark users the certificate rejects."""
     lib = require_cuda()
-    n_users, d = user_repr.shape
+    n_users = users.n_rows
     n_lists = theta.numel() // max(n_users, 1)
     width = cand_item.shape[-1]
-    dev = user_repr.device
-    out_s = torch.empty((n_users, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((n_users, k), dtype=torch.int32, device=dev)
+    dev = users.split.device
+    if out is None:
+        out = PackedTopK(n_users, k, dev)
     out_f = torch.empty((n_users,), dtype=torch.int32, device=dev)
-    rc = lib.trk_rescore_topk_f32(_p(user_repr), _p(item_repr), _p(user_bias), _p(item_bias), _p(cand_item), _p(theta),
-                                  _p(flags), _p(user_norm), _p(item_stats), n_users, item_repr.shape[0], d, n_lists,
-                                  width, int(k), int(item_id_offset), _p(out_s), _p(out_i), _p(out_f), _stream())
-    _lib.check(rc, 'trk_rescore_topk_f32')
-    return out_s, out_i, out_f
+    rc = lib.trk_rescore_topk_split(_p(users.split), _p(users.scale), _p(items.split), _p(items.scale), _p(users.bias),
+                                    _p(items.bias), _p(cand_item), _p(theta), _p(user_norm), _p(item_stats), n_users,
+                                    items.n_rows, int(users.d_pad), n_lists, width, int(k), int(item_id_offset),
+                                    out.score_ptr(), out.item_ptr(), 2 * out.k, _p(out_f), _stream())
+    _lib.check(rc, 'trk_rescore_topk_split')
+    return out, out_f
 
 
 class _HostResults(object):
@@ -429,64 +514,96 @@ def to_host(*tensors):
 
 
 class SideOperands(object):
-    """Everything the score kernels need from one side (users or items), all resident on the device."""
+    """Everything the score kernels need from one side (users or items), all resident on the device.
+    norm: row norms (users, filter path); stats: float32[3] max norm / max scale / max |bias| (items, filter path)."""
 
-    def __init__(self, repr_f32, split, scale, bias, n_rows, d, d_pad):
+    def __init__(self, repr_f32, split, scale, bias, n_rows, d, d_pad, norm=None, stats=None):
         self.repr_f32, self.split, self.scale, self.bias = repr_f32, split, scale, bias
         self.n_rows, self.d, self.d_pad = n_rows, d, d_pad
+        self.norm, self.stats = norm, stats
+
+    def rows(self, r0, r1):
+        """The operands of rows [r0, r1) (views)."""
+        cut = lambda t: None if t is None else t[r0:r1]   # noqa: E731
+        return SideOperands(cut(self.repr_f32), cut(self.split), cut(self.scale), cut(self.bias), r1 - r0, self.d,
+                            self.d_pad, norm=cut(self.norm), stats=self.stats)
 
 
-def topk_exact(users, items, k, n_splits=None, item_id_offset=0):
-    """Exact 3-pass fused kernel + merge: ([U, k] scores, [U, k] ids)."""
+def topk_exact(users, items, k, n_splits=None, item_id_offset=0, out=None, n_users_live=None):
+    """Exact 3-pass fused kernel + merge -> PackedTopK [U, k]."""
     meta = pack_item_meta(items.scale, items.bias, items.n_rows)
     cs, ci = score_topk(users.split, users.scale, users.bias, items.split, meta, users.n_rows, items.n_rows,
-                        users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset)
-    return topk_merge(cs, ci, k)
+                        users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset, n_users_live=n_users_live)
+    return topk_merge(cs, ci, k, out=out, n_users_live=n_users_live)
 
 
 class FilterItems(object):
-    """Item-side inputs of the filter kernel, derived once per call from the K1 outputs."""
+    """Item-side inputs of the filter kernel, derived once per call from the K1 outputs (items.stats: max norm / max
+    scale already formed in K1's epilogue; operands from a user-defined graph get them from trk_operand_stats)."""
 
     def __init__(self, items):
         dev = items.split.device
-        self.stats = torch.zeros((3,), dtype=torch.float32, device=dev)
-        operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=self.stats)
+        if items.stats is not None:
+            self.stats = items.stats
+        else:
+            self.stats = torch.zeros((3,), dtype=torch.float32, device=dev)
+            operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=self.stats)
         self.perm = bias_processing_order(items.bias)
         self.hi = rescale_hi_global(items.split, items.scale, self.stats, items.d_pad, perm=self.perm)
-        self.bias_pad, self.block_max = pack_item_bias(items.bias, items.n_rows, self.stats, dev, perm=self.perm)
+        self.bias_pad, self.block_max, self.block_min = pack_item_bias(items.bias, items.n_rows, self.stats, dev,
+                                                                       perm=self.perm, want_min=True)
 
 
-def filter_and_rescore(users, items, fitems, user_norm, k, n_splits=None, item_id_offset=0):
-    """(top scores [U,k], top ids [U,k], flags [U]) -- flags mark users the certificate did not cover."""
-    cs, ci, theta, flags = score_filter(users.split, users.scale, users.bias, user_norm, fitems.hi, fitems.stats,
-                                        fitems.bias_pad, fitems.block_max, fitems.perm, users.n_rows, items.n_rows,
-                                        users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset)
-    return rescore_topk(users.repr_f32, items.repr_f32, users.bias, items.bias, ci, theta, flags, user_norm,
-                        fitems.stats, k, item_id_offset=item_id_offset)
+def filter_and_rescore(users, items, fitems, user_norm, k, n_splits=None, item_id_offset=0, out=None):
+    """(PackedTopK [U, k], flags [U]) -- flags mark users the certificate did not cover."""
+    _, ci, theta = score_filter(users.split, users.scale, users.bias, user_norm, fitems.hi, fitems.stats,
+                                fitems.bias_pad, fitems.block_max, fitems.perm, users.n_rows, items.n_rows,
+                                users.d_pad, k, n_splits=n_splits, item_id_offset=item_id_offset,
+                                block_bias_min=fitems.block_min)
+    return rescore_topk(users, items, ci, theta, user_norm, fitems.stats, k, item_id_offset=item_id_offset, out=out)
 
 
-def rerun_uncertified(users, items, bad, top_s, top_i, k, item_id_offset=0):
-    """Users flagged by the certificate go through the exact kernel; returns how many there were (one host sync)."""
-    n_bad = int(bad.sum().item())
-    if n_bad:
-        idx = bad.nonzero(as_tuple=True)[0]
-        sub = SideOperands(None, users.split.index_select(0, idx).contiguous(), users.scale.index_select(0, idx),
-                           None if users.bias is None else users.bias.index_select(0, idx), int(idx.numel()), users.d,
-                           users.d_pad)
-        ex_s, ex_i = topk_exact(sub, items, k, item_id_offset=item_id_offset)
-        top_s.index_copy_(0, idx, ex_s)
-        top_i.index_copy_(0, idx, ex_i)
-    return n_bad
+def fallback_capacity(n_users):
+    """Rows the device-side fallback can hold (the exact kernel is launched over this many rows and skips the unused
+    ones): 1/8 of the batch, at least 1024, whole 128-row user blocks.  More flagged rows than this = a tie-heavy
+    batch; the host layer then re-runs the whole batch through the exact kernel."""
+    cap = min(int(n_users), max(1024, int(n_users) // 8))
+    return ((cap + 127) // 128) * 128
 
 
-def topk_filter(users, items, k, n_splits=None, item_id_offset=0, info=None):
-    """Filter form: one tensor pass + exact fp32 re-scoring; users whose error bound cannot be certified (buffer
-    overflow under massive ties, bound violated) are re-run through the exact kernel.  Needs users/items.repr_f32."""
-    user_norm = operand_stats(users.split, users.scale, users.d_pad)
-    fitems = FilterItems(items)
-    top_s, top_i, bad = filter_and_rescore(users, items, fitems, user_norm, k, n_splits=n_splits,
-                                           item_id_offset=item_id_offset)
-    n_bad = rerun_uncertified(users, items, bad, top_s, top_i, k, item_id_offset=item_id_offset)
-    if info is not None:
-        info['fallback_rows'] = n_bad
-    return top_s, top_i
+def rerun_uncertified(users, items, bad, top, k, item_id_offset=0):
+    """Users flagged by the certificate go through the exact kernel WITHOUT a host round trip: the flagged rows are
+    compacted on the device, their operands gathered into a fixed-capacity buffer, the exact kernel runs over that buffer
+    with the device-side count and the rows are scattered back into `top`.  Returns counters (device int32[2]):
+    [0] = flagged rows; > capacity means overflow (the caller checks it at its next synchronisation)."""
+    lib = require_cuda()
+    dev = users.split.device
+    cap = fallback_capacity(users.n_rows)
+    idx = torch.empty((cap,), dtype=torch.int32, device=dev)
+    counters = torch.empty((2,), dtype=torch.int32, device=dev)
+    rc = lib.trk_select_flagged_rows(_p(bad), users.n_rows, _p(idx), cap, _p(counters), _stream())
+    _lib.check(rc, 'trk_select_flagged_rows')
+    sub_split = torch.empty((cap, 2 * users.d_pad), dtype=torch.float16, device=dev)
+    sub_scale = torch.empty((cap,), dtype=torch.float32, device=dev)
+    sub_bias = None if users.bias is None else torch.empty((cap,), dtype=torch.float32, device=dev)
+    rc = lib.trk_gather_operand_rows(_p(idx), _p(counters), cap, _p(users.split), _p(users.scale), _p(users.bias),
+                                     int(users.d_pad), _p(sub_split), _p(sub_scale), _p(sub_bias), _stream())
+    _lib.check(rc, 'trk_gather_operand_rows')
+    sub = SideOperands(None, sub_split, sub_scale, sub_bias, cap, users.d, users.d_pad)
+    exact = topk_exact(sub, items, k, item_id_offset=item_id_offset, n_users_live=counters)
+    rc = lib.trk_scatter_topk_rows(_p(idx), _p(counters), cap, exact.score_ptr(), exact.item_ptr(), 2 * exact.k, int(k),
+                                   top.score_ptr(), top.item_ptr(), 2 * top.k, _stream())
+    _lib.check(rc, 'trk_scatter_topk_rows')
+    return counters, cap
+
+
+def topk_filter(users, items, k, n_splits=None, item_id_offset=0, fitems=None):
+    """Filter form: one tensor pass + re-scoring from the split operands; users whose error bound cannot be certified
+    (buffer overflow under massive ties, bound violated) are re-run through the exact kernel on the device.
+    Returns (PackedTopK, counters device int32[2], capacity)."""
+    user_norm = users.norm if users.norm is not None else operand_stats(users.split, users.scale, users.d_pad)
+    if fitems is None:
+        fitems = FilterItems(items)
+    top, bad = filter_and_rescore(users, items, fitems, user_norm, k, n_splits=n_splits, item_id_offset=item_id_offset)
+    counters, cap = rerun_uncertified(users, items, bad, top, k, item_id_offset=item_id_offset)
+    return top, counters, cap

@@ -436,13 +436,13 @@ class TensorRec(object):
                 side, sparse_input.shape[1], n_features))
 
     def _represent(self, graph, sparse_input, n_features, node_name_ending, device, extra_normalize=0,
-                   want_f32=True, split_d_pad=None):
-        """One representation on the device: (repr_f32 | None, split | None, scale | None)."""
+                   want_f32=True, split_d_pad=None, want_norm=False, stats=None):
+        """One representation on the device: (repr_f32 | None, split | None, scale | None[, norm])."""
         if type(graph) in _BUILTIN_REPR:
             weights = self._var(LinearRepresentationGraph.weight_name(node_name_ending), device)
             n_norm = (1 if graph.b200_kind == 'normalized_linear' else 0) + extra_normalize
             return kernels.gather_reduce(sparse_input.device_csr(device), weights, n_normalize=n_norm,
-                                         want_f32=want_f32, split_d_pad=split_d_pad)
+                                         want_f32=want_f32, split_d_pad=split_d_pad, want_norm=want_norm, stats=stats)
         # user-defined / non-linear plugin: run its own forward on the device, then hand the dense rows to the kernels
         with torch.no_grad(), variable_scope(self._variables):
             for k in list(self._variables):
@@ -456,6 +456,12 @@ class TensorRec(object):
         split = scale = None
         if split_d_pad is not None:
             split, scale = kernels.split_f32(dense, n_normalize=0, d_pad=split_d_pad)
+        if stats is not None:
+            stats.zero_()
+        if want_norm or stats is not None:
+            norm = kernels.operand_stats(split, scale, split_d_pad, want_norm=want_norm, stats=stats)
+            if want_norm:
+                return (dense if want_f32 else None), split, scale, norm
         return (dense if want_f32 else None), split, scale
 
     def _projected_biases(self, sparse_input, name, device):
@@ -471,21 +477,30 @@ class TensorRec(object):
             raise RuntimeError('TENSORREC_B200_SCORE_PATH=tensor but this model cannot use the tcgen05 kernel')
         return ok
 
-    def _tensor_operands(self, user_in, item_in, device, want_f32=False):
-        """Both sides as kernels.SideOperands: split-fp16 operands + scales (+ fp32 representations), biases."""
+    def _side_operands(self, side, sparse_in, device, for_filter=False):
+        """One side ('user' or 'item') as kernels.SideOperands: split-fp16 operand + scale, projected biases and -- for
+        the filter form of the fused top-k -- the row norms (users) / the global statistics (items), all from K1."""
         extra = 1 if type(self.prediction_graph_factory) is CosineSimilarityPredictionGraph else 0
         d_pad = kernels.d_pad_for(self.n_components)
-        u32, user_split, user_scale = self._represent(self.user_repr_graph_factory, user_in, self.n_user_features,
-                                                      'user_0', device, extra, want_f32=want_f32, split_d_pad=d_pad)
-        i32, item_split, item_scale = self._represent(self.item_repr_graph_factory, item_in, self.n_item_features,
-                                                      'item', device, extra, want_f32=want_f32, split_d_pad=d_pad)
-        user_bias = item_bias = None
+        is_user = side == 'user'
+        graph = self.user_repr_graph_factory if is_user else self.item_repr_graph_factory
+        n_features = self.n_user_features if is_user else self.n_item_features
+        stats = norm = None
+        if for_filter and not is_user:
+            stats = torch.empty((3,), dtype=torch.float32, device=device)
+        out = self._represent(graph, sparse_in, n_features, 'user_0' if is_user else 'item', device, extra,
+                              want_f32=False, split_d_pad=d_pad, want_norm=for_filter and is_user, stats=stats)
+        split, scale = out[1], out[2]
+        if for_filter and is_user:
+            norm = out[3]
+        bias = None
         if self.biased:
-            user_bias = self._projected_biases(user_in, 'feature_biases_user', device)
-            item_bias = self._projected_biases(item_in, 'feature_biases_item', device)
-        users = kernels.SideOperands(u32, user_split, user_scale, user_bias, user_in.shape[0], self.n_components, d_pad)
-        items = kernels.SideOperands(i32, item_split, item_scale, item_bias, item_in.shape[0], self.n_components, d_pad)
-        return users, items
+            bias = self._projected_biases(sparse_in, 'feature_biases_user' if is_user else 'feature_biases_item', device)
+        return kernels.SideOperands(None, split, scale, bias, sparse_in.shape[0], self.n_components, d_pad, norm=norm,
+                                    stats=stats)
+
+    def _tensor_operands(self, user_in, item_in, device):
+        return self._side_operands('user', user_in, device), self._side_operands('item', item_in, device)
 
     def _predict_device(self, user_in, item_in, device):
         """tf_prediction: dense float32 scores [n_users, n_items] on the device."""
@@ -562,12 +577,18 @@ class TensorRec(object):
             return np.zeros(tuple(scores.shape), dtype=np.int32)
         return kernels.to_host(kernels.rank_full(scores))
 
-    def predict_top_k(self, user_features, item_features, k, item_id_offset=0, gather_group=None, to_host=True):
+    def predict_top_k(self, user_features, item_features, k, item_id_offset=0, gather_group=None, to_host=True,
+                      gather='all', user_batch_size=None):
         """The k best items per user in reference rank order, without materialising the score matrix.
 
-        Single GPU: K2+K3 fused kernel + merge.  Item axis sharded over ranks (`gather_group` = a torch.distributed
-        process group whose ranks each pass THEIR rows of item_features and the global id of the first one as
-        item_id_offset): one all-gather of the per-shard candidates, then the same merge on every rank."""
+        Single GPU: K2+K3 fused kernel (filter form: one tensor pass + re-scoring of the survivors; users the
+        certificate rejects go through the exact kernel on the device) -> TopK(items, scores) for every user.
+        Item axis sharded over ranks (`gather_group` = a torch.distributed process group whose ranks each pass THEIR
+        rows of item_features and the global id of the first one as item_id_offset): one all-to-all of the per-shard
+        top-k -- rank r receives the candidates of ITS slice of the users from every shard and merges them -- and,
+        with gather='all', one all-gather of the merged slices so that every rank returns all users.  gather='slice'
+        returns this rank's users only (rows `last_topk_info['user_rows']`).
+        user_batch_size: users are processed in blocks of this many rows (bounds device memory at 10M+ users)."""
         if self.tf_prediction is None:
             raise ModelNotFitException(method='predict_rank')
         device = self._cuda_device()
@@ -579,38 +600,97 @@ class TensorRec(object):
         k = int(k)
         if k < 1:
             raise ValueError('k must be >= 1')
+        if gather not in ('all', 'slice'):
+            raise ValueError("gather must be 'all' or 'slice'")
         if n_users == 0:
             return TopK(np.zeros((0, k), np.int32), np.zeros((0, k), np.float32))
+        from . import distributed
 
         fused = self._tensor_path_ok() and k <= kernels.topk_max_k(kernels.d_pad_for(self.n_components)) and n_items > 0
+        use_filter = fused and TOPK_PATH != 'exact' and k <= kernels.filter_max_k()
+        info = self.last_topk_info = {'path': 'filter' if use_filter else ('exact3' if fused else 'dense+rank'),
+                                      'fallback_rows': 0}
+        items = fitems = None
         if fused:
-            use_filter = TOPK_PATH != 'exact' and k <= kernels.filter_max_k()
-            users, items = self._tensor_operands(user_in, item_in, device, want_f32=use_filter)
+            items = self._side_operands('item', item_in, device, for_filter=use_filter)
             if use_filter:
-                self.last_topk_info = {}
-                top_s, top_i = kernels.topk_filter(users, items, k, item_id_offset=item_id_offset,
-                                                   info=self.last_topk_info)
-            else:
-                top_s, top_i = kernels.topk_exact(users, items, k, item_id_offset=item_id_offset)
+                fitems = kernels.FilterItems(items)
+
+        if user_batch_size is None or user_batch_size >= n_users:
+            blocks = [(0, n_users, user_in)]
         else:
-            # any model the fused kernel does not cover: dense scores -> exact full ranks -> the rank <= k entries
-            scores = self._predict_device(user_in, item_in, device)
-            top_s = torch.full((n_users, k), float('-inf'), device=device)
-            top_i = torch.full((n_users, k), 2 ** 31 - 1, dtype=torch.int32, device=device)
-            if n_items > 0:
-                ranks = kernels.rank_full(scores).long()
-                sel = ranks <= k
-                rows, cols = sel.nonzero(as_tuple=True)
-                pos = ranks[rows, cols] - 1
-                top_s[rows, pos] = scores[rows, cols]
-                top_i[rows, pos] = (cols + item_id_offset).to(torch.int32)
-        if gather_group is not None:
-            from .distributed import all_gather_candidates
-            all_s, all_i = all_gather_candidates(top_s, top_i, gather_group)
-            top_s, top_i = kernels.topk_merge(all_s, all_i, k)
+            step = max(1, int(user_batch_size))
+            csr = user_in.matrix if isinstance(user_in.matrix, sp.csr_matrix) else sp.csr_matrix(user_in.matrix)
+            blocks = [(u0, min(n_users, u0 + step), SparseInput(csr[u0:min(n_users, u0 + step)]))
+                      for u0 in range(0, n_users, step)]
+
+        def run_block(block_in, force_exact=False):
+            if fused:
+                users = self._side_operands('user', block_in, device, for_filter=use_filter and not force_exact)
+                if use_filter and not force_exact:
+                    return kernels.topk_filter(users, items, k, item_id_offset=item_id_offset, fitems=fitems)
+                return kernels.topk_exact(users, items, k, item_id_offset=item_id_offset), None, 0
+            return self._topk_from_dense(block_in, item_in, k, item_id_offset, device), None, 0
+
+        def exchange(top, u0, u1):
+            if gather_group is None:
+                return top, np.arange(u0, u1)
+            merged, (lo, hi) = distributed.exchange_and_merge(top, gather_group)
+            if gather == 'all':
+                return distributed.all_gather_rows(merged, u1 - u0, gather_group), np.arange(u0, u1)
+            return merged, np.arange(u0 + lo, u0 + hi)
+
+        results, counters, rows = [], [], []
+        for (u0, u1, block_in) in blocks:
+            top, cnt, cap = run_block(block_in)
+            top, user_rows = exchange(top, u0, u1)
+            results.append(top)
+            counters.append((cnt, cap))
+            rows.append(user_rows)
+
+        # one synchronisation for the whole call: how many rows the certificate rejected per block (device counters);
+        # a block with more rejected rows than the device-side fallback holds is re-run through the exact kernel
+        live = [c for c, _ in counters if c is not None]
+        if live:
+            counts = torch.stack([c[0] for c in live]).cpu().numpy().tolist()
+            counts = iter(counts)
+            overflow = []
+            for b, (c, cap) in enumerate(counters):
+                if c is None:
+                    continue
+                n_bad = next(counts)
+                info['fallback_rows'] += min(n_bad, cap)
+                if n_bad > cap:
+                    overflow.append(b)
+            if gather_group is not None:     # every rank must take the same decision: the exchange is collective
+                overflow = distributed.union_of_indices(overflow, len(blocks), gather_group, device)
+            for b in overflow:
+                u0, u1, block_in = blocks[b]
+                top, _, _ = run_block(block_in, force_exact=True)
+                results[b], rows[b] = exchange(top, u0, u1)
+            info['overflow_blocks'] = len(overflow)
+        info['user_rows'] = rows[0] if len(rows) == 1 else np.concatenate(rows)
+        top_s = results[0].scores if len(results) == 1 else torch.cat([r.scores for r in results])
+        top_i = results[0].items if len(results) == 1 else torch.cat([r.items for r in results])
         if not to_host:
             return TopK(top_i, top_s)
         return TopK(*kernels.to_host(top_i, top_s))
+
+    def _topk_from_dense(self, user_in, item_in, k, item_id_offset, device):
+        """Any model the fused kernel does not cover: dense scores -> exact full ranks -> the rank <= k entries."""
+        n_users, n_items = user_in.shape[0], item_in.shape[0]
+        top = kernels.PackedTopK(n_users, k, device)
+        top.scores.fill_(float('-inf'))
+        top.items.fill_(2 ** 31 - 1)
+        if n_items > 0:
+            scores = self._predict_device(user_in, item_in, device)
+            ranks = kernels.rank_full(scores).long()
+            sel = ranks <= k
+            rows, cols = sel.nonzero(as_tuple=True)
+            pos = ranks[rows, cols] - 1
+            top.scores[rows, pos] = scores[rows, cols]
+            top.items[rows, pos] = (cols + item_id_offset).to(torch.int32)
+        return top
 
     def predict_similar_items(self, item_features, item_ids, n_similar):
         """tensorrec/tensorrec.py:666-703: for each id, the n_similar (item_id, score) pairs of highest prediction

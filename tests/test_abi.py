@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), 'libtensorrec_b200.so does not export %s' % name
         assert name in _lib.SIGNATURES, 'ctypes binding misses %s' % name
     assert set(_lib.SIGNATURES) == set(declared_symbols())
-    assert lib.trk_version() == 1000
+    assert lib.trk_version() == 2000
     assert lib.trk_score_topk_max_k(128) >= 10 and lib.trk_score_topk_max_k(96) == 0
     assert lib.trk_rank_full_workspace_bytes(10, 100) == 0
     assert lib.trk_rank_full_workspace_bytes(3, 5000) == 2 * 3 * 2 * 4096 * 8     # two ping-pong key buffers
@@ -40,7 +40,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_argument_errors_are_reported_through_the_abi():
     from tensorrec_b200 import _lib
     lib = _lib.load()
-    rc = lib.trk_csr_gather_reduce_f32(None, None, None, None, 4, 4, 4, 0, None, None, 0, None, None)
+    rc = lib.trk_csr_gather_reduce_f32(None, None, None, None, 4, 4, 4, 0, None, None, 0, None, None, None, None)
     assert rc == _lib.TRK_ERR_ARG
     assert 'null' in _lib.last_error()
     with pytest.raises(ValueError):

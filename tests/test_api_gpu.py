@@ -334,3 +334,73 @@ def test_training_matmul_runs_on_k1_and_matches_torch_sparse(T):
     model = T.TensorRec(n_components=8)
     model.fit(interactions, uf, itf, epochs=30, learning_rate=.05)
     assert np.all(np.isfinite(model.predict(uf, itf)))
+
+
+@pytest.mark.parametrize('integer', [True, False])
+def test_item_shards_run_one_after_the_other_through_predict_top_k(T, integer):
+    """The multi-GPU layout on ONE GPU (the driver's test box has one): every item shard goes through
+    predict_top_k(item_id_offset=...) -- filter path, device-side fallback -- and the per-shard results are merged in the
+    layout the all-to-all delivers ([shards, U_slice, 2k], trk_topk_merge with list / user strides).  Equals the oracle
+    and the unsharded call."""
+    import torch
+    from tensorrec_b200 import kernels
+    from tensorrec_b200.distributed import shard_bounds
+    U, I, d, k, world = 517, 9001, 128, 10, 4
+    uf = H.tag_features(U, 200, 20, seed=1, integer=integer) if integer else H.indicator_features(U, seed=1)
+    itf = H.tag_features(I, 200, 20, seed=2, integer=integer) if integer else H.indicator_features(I, seed=2)
+    wu = H.linear_weights(uf.shape[1], d, seed=3, integer=integer)
+    wi = H.linear_weights(itf.shape[1], d, seed=4, integer=integer)
+    bu = H.feature_biases(uf.shape[1], seed=5, integer=integer)
+    bi = H.feature_biases(itf.shape[1], seed=6, integer=integer)
+    model = T.TensorRec(n_components=d)
+    model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
+                       'feature_biases_item': bi[:, None]})
+    whole = model.predict_top_k(uf, itf, k)
+    assert model.last_topk_info['path'] == 'filter'
+    per_shard = []
+    for r in range(world):
+        lo, hi = shard_bounds(I, world, r)
+        top = model.predict_top_k(uf, sp.csr_matrix(itf)[lo:hi], k, item_id_offset=lo, to_host=False)
+        per_shard.append(torch.cat([top.scores.view(torch.int32), top.items], dim=1))      # PackedTopK rows [U, 2k]
+    items_out, scores_out = [], []
+    for r in range(world):                       # rank r's user slice, merged from every shard's rows of that slice
+        u0, u1 = shard_bounds(U, world, r)
+        recv = torch.stack([p[u0:u1] for p in per_shard]).contiguous()                     # [shards, U_slice, 2k]
+        merged = kernels.topk_merge_received(recv, u1 - u0, world, k)
+        items_out.append(merged.items.cpu().numpy())
+        scores_out.append(merged.scores.cpu().numpy())
+    got_i, got_s = np.concatenate(items_out), np.concatenate(scores_out)
+    scores = oracle.OracleModel([wu], wi, bu, bi).predict(uf, itf)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    if integer:
+        assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
+        assert np.array_equal(whole.items, exp_i) and np.array_equal(whole.scores, exp_s)
+    else:
+        assert np.array_equal(got_i, whole.items) and np.array_equal(got_s, whole.scores)   # sharding changes nothing
+        assert (got_i != exp_i).mean() < 0.01
+
+
+def test_predict_top_k_user_batches_equal_one_batch(T):
+    U, I, d, k = 1000, 3000, 64, 10
+    uf, itf = H.indicator_features(U, seed=1), H.indicator_features(I, seed=2)
+    wu, wi = H.linear_weights(uf.shape[1], d, seed=3), H.linear_weights(itf.shape[1], d, seed=4)
+    bu, bi = H.feature_biases(uf.shape[1], seed=5), H.feature_biases(itf.shape[1], seed=6)
+    model = T.TensorRec(n_components=d)
+    model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
+                       'feature_biases_item': bi[:, None]})
+    one = model.predict_top_k(uf, itf, k)
+    many = model.predict_top_k(uf, itf, k, user_batch_size=300)
+    assert np.array_equal(one.items, many.items) and np.array_equal(one.scores, many.scores)
+    assert np.array_equal(model.last_topk_info['user_rows'], np.arange(U))
+
+
+def test_wide_representations_are_tiled_over_k1(T):
+    """n_components beyond one K1 launch (> 512 columns): the component axis is tiled, values equal the oracle's."""
+    U, I, d = 40, 60, 640
+    uf, itf = H.tag_features(U, 50, 5, seed=1, integer=True), H.tag_features(I, 50, 5, seed=2, integer=True)
+    wu, wi = H.linear_weights(50, d, seed=3, integer=True), H.linear_weights(50, d, seed=4, integer=True)
+    model = T.TensorRec(n_components=d, biased=False)
+    model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi})
+    om = oracle.OracleModel([wu], wi)
+    assert np.array_equal(model.predict_user_representation(uf), om.user_representation(uf)[0])
+    assert np.array_equal(model.predict(uf, itf), om.predict(uf, itf))

@@ -1,5 +1,7 @@
-"""Multi-GPU test of the item-sharded predict_rank(k): one process per GPU, NCCL all-gather of the
-per-shard candidates, merge on every rank == the single-GPU / oracle answer.  Skipped on boxes with < 2 GPUs."""
+"""Multi-GPU test of the item-sharded predict_rank(k): one process per GPU, one NCCL all-to-all of the
+per-shard top-k, every rank merges its user slice (gather='slice'), optionally followed by an all-gather of the merged
+slices (gather='all') == the oracle answer.  Skipped on boxes with < 2 GPUs (tests/test_api_gpu.py runs the same shards
+one after the other on one GPU through the same entry points)."""
 import os
 import socket
 import sys
@@ -25,7 +27,7 @@ def _worker(rank, world, port, out_dir):
     import torch.distributed as dist
     import oracle
     import tensorrec_b200 as T
-    from tensorrec_b200.distributed import sharded_predict_top_k
+    from tensorrec_b200.distributed import predict_top_k_sharded, shard_bounds
     from tests import helpers as H
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -41,15 +43,22 @@ def _worker(rank, world, port, out_dir):
             model = T.TensorRec(n_components=d)
             model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi,
                                'feature_biases_user': bu[:, None], 'feature_biases_item': bi[:, None]})
-            top = sharded_predict_top_k(model, uf, itf, k)
             scores = oracle.OracleModel([wu], wi, bu, bi).predict(uf, itf)
             exp_i, exp_s = oracle.top_k_from_scores(scores, k)
-            if integer:
-                assert np.array_equal(top.items, exp_i) and np.array_equal(top.scores, exp_s)
-            else:
-                rows = np.arange(U)[:, None]
-                assert np.all(np.abs(top.scores - scores[rows, top.items]) <= 1e-5 * 40 + 2e-6)
-                assert (top.items != exp_i).mean() < 0.01
+            for gather, batch in (('all', None), ('slice', None), ('slice', 128)):
+                top = predict_top_k_sharded(model, uf, itf, k, gather=gather, user_batch_size=batch)
+                rows_of = model.last_topk_info['user_rows']
+                if gather == 'all':
+                    assert np.array_equal(rows_of, np.arange(U))
+                elif batch is None:
+                    lo, hi = shard_bounds(U, world, rank)
+                    assert np.array_equal(rows_of, np.arange(lo, hi))
+                assert top.items.shape == (len(rows_of), k)
+                if integer:
+                    assert np.array_equal(top.items, exp_i[rows_of]) and np.array_equal(top.scores, exp_s[rows_of])
+                else:
+                    assert np.all(np.abs(top.scores - scores[rows_of[:, None], top.items]) <= 1e-5 * 40 + 2e-6)
+                    assert (top.items != exp_i[rows_of]).mean() < 0.01
         open(os.path.join(out_dir, 'ok_%d' % rank), 'w').write('ok')
     finally:
         dist.destroy_process_group()

@@ -236,8 +236,8 @@ def run_fused(K, uf, itf, wu, wi, bu, bi, k, n_splits=None, n_norm=0, offset=0):
     meta = K.pack_item_meta(isc, ib, itf.shape[0])
     cs, ci = K.score_topk(us, usc, ub, its, meta, uf.shape[0], itf.shape[0], d_pad, k, n_splits=n_splits,
                           item_id_offset=offset)
-    top_s, top_i = K.topk_merge(cs, ci, k)
-    return top_s.cpu().numpy(), top_i.cpu().numpy(), (us, usc, ub, its, meta, d_pad)
+    top = K.topk_merge(cs, ci, k)
+    return top.scores.cpu().numpy(), top.items.cpu().numpy(), (us, usc, ub, its, meta, d_pad)
 
 
 def oracle_scores(uf, itf, wu, wi, bu, bi, prediction='dot'):
@@ -296,8 +296,8 @@ def test_fused_topk_offset_and_sharded_merge(K):
         s, i, _ = run_fused(K, uf, itf[lo:hi], wu, wi, bu, bi, k, offset=lo)
         cs.append(torch.from_numpy(s).cuda())
         ci.append(torch.from_numpy(i).cuda())
-    ms, mi = K.topk_merge(torch.stack(cs, 1), torch.stack(ci, 1), k)
-    assert np.array_equal(mi.cpu().numpy(), exp_i) and np.array_equal(ms.cpu().numpy(), exp_s)
+    top = K.topk_merge(torch.stack(cs, 1), torch.stack(ci, 1), k)
+    assert np.array_equal(top.items.cpu().numpy(), exp_i) and np.array_equal(top.scores.cpu().numpy(), exp_s)
 
 
 def test_fused_topk_k_larger_than_items_pads_with_sentinels(K):
@@ -326,9 +326,30 @@ def test_topk_merge_orders_ties_by_lower_id(K):
     import torch
     s = torch.tensor([[[5., 3., 1.], [5., 4., 1.], [9., 1., -float('inf')]]], device='cuda')
     i = torch.tensor([[[7, 1, 30], [2, 9, 11], [40, 10, 2 ** 31 - 1]]], dtype=torch.int32, device='cuda')
-    ms, mi = K.topk_merge(s, i, 6)
-    assert mi.cpu().tolist() == [[40, 2, 7, 9, 1, 10]]
-    assert ms.cpu().tolist() == [[9., 5., 5., 4., 3., 1.]]
+    top = K.topk_merge(s, i, 6)
+    assert top.items.cpu().tolist() == [[40, 2, 7, 9, 1, 10]]
+    assert top.scores.cpu().tolist() == [[9., 5., 5., 4., 3., 1.]]
+
+
+def test_topk_merge_of_the_exchange_receive_layout(K):
+    """[n_lists, U_slice, 2k] (what the all-to-all delivers) merges to the same result as the [U, L, k] layout."""
+    import torch
+    rng = np.random.default_rng(5)
+    U, L, k = 77, 5, 10
+    scores = np.sort(rng.integers(-4, 5, size=(U, L, k)).astype(F32), axis=2)[:, :, ::-1].copy()
+    ids = np.stack([np.stack([np.sort(rng.choice(1000, k, replace=False)) + 1000 * l for l in range(L)])
+                    for _ in range(U)]).astype(np.int32)
+    # equal scores inside a list must be ordered by id: sort ids within runs of equal score
+    for u in range(U):
+        for l in range(L):
+            order = np.lexsort((ids[u, l], -scores[u, l]))
+            scores[u, l], ids[u, l] = scores[u, l][order], ids[u, l][order]
+    ref = K.topk_merge(dev(scores), dev(ids), k)
+    recv = np.empty((L, U, 2 * k), dtype=np.int32)
+    recv[:, :, :k] = scores.view(np.int32).transpose(1, 0, 2)
+    recv[:, :, k:] = ids.transpose(1, 0, 2)
+    got = K.topk_merge_received(dev(recv), U, L, k)
+    assert torch.equal(got.buf, ref.buf)
 
 
 def test_unsupported_shapes_raise(K):
@@ -340,19 +361,24 @@ def test_unsupported_shapes_raise(K):
 
 # ------------------------------------------------------------------------------------------------- filter + rescore
 def side_operands(K, feats, w, b, d, n_norm=0):
+    """Operands as the host layer builds them for the filter path: norms and statistics come out of K1."""
+    import torch
     csr = K.DeviceCSR.from_scipy(feats)
     d_pad = K.d_pad_for(d)
-    f32, split, scale = K.gather_reduce(csr, dev(w), n_normalize=n_norm, want_f32=True, split_d_pad=d_pad)
+    stats = torch.empty(3, device='cuda')
+    f32, split, scale, norm = K.gather_reduce(csr, dev(w), n_normalize=n_norm, want_f32=True, split_d_pad=d_pad,
+                                              want_norm=True, stats=stats)
     bias = K.project_biases(csr, dev(b)) if b is not None else None
-    return K.SideOperands(f32, split, scale, bias, feats.shape[0], d, d_pad)
+    return K.SideOperands(f32, split, scale, bias, feats.shape[0], d, d_pad, norm=norm, stats=stats)
 
 
 def run_filter(K, uf, itf, wu, wi, bu, bi, k, n_splits=None, n_norm=0, offset=0):
     users = side_operands(K, uf, wu, bu, wu.shape[1], n_norm)
     items = side_operands(K, itf, wi, bi, wi.shape[1], n_norm)
-    info = {}
-    s, i = K.topk_filter(users, items, k, n_splits=n_splits, item_id_offset=offset, info=info)
-    return s.cpu().numpy(), i.cpu().numpy(), info
+    top, counters, cap = K.topk_filter(users, items, k, n_splits=n_splits, item_id_offset=offset)
+    n_bad = int(counters[0])
+    assert n_bad <= cap, 'device-side fallback overflowed in a test-sized batch'
+    return top.scores.cpu().numpy(), top.items.cpu().numpy(), {'fallback_rows': n_bad}
 
 
 def test_operand_stats_and_global_rescale(K):
@@ -365,6 +391,10 @@ def test_operand_stats_and_global_rescale(K):
     assert np.all(norm >= true) and np.all(norm <= true * 1.01 + 1e-30)           # upper bounds, tight
     st = stats.cpu().numpy()
     assert st[0] == norm.max() and st[1] == items.scale.cpu().numpy().max()
+    # the same quantities straight out of K1's epilogue (what the host layer uses): upper bounds, equally tight
+    k1_norm, k1_st = items.norm.cpu().numpy(), items.stats.cpu().numpy()
+    assert np.all(k1_norm >= true) and np.all(k1_norm <= true * 1.01 + 1e-30)
+    assert k1_st[0] == k1_norm.max() and k1_st[1] == st[1]
     hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad).float().cpu().numpy()
     x = items.repr_f32.cpu().numpy()
     rec = hi[:, :100] * st[1]
@@ -437,14 +467,14 @@ def test_filter_candidates_respect_the_error_bound(K, sort_by_bias):
     K.operand_stats(items.split, items.scale, items.d_pad, want_norm=False, stats=stats)
     perm = K.bias_processing_order(items.bias) if sort_by_bias else None
     hi = K.rescale_hi_global(items.split, items.scale, stats, items.d_pad, perm=perm)
-    bias_pad, bmax = K.pack_item_bias(items.bias, I, stats, 'cuda', perm=perm)
-    cs, ci, theta, flags = K.score_filter(users.split, users.scale, users.bias, unorm, hi, stats, bias_pad, bmax, perm,
-                                          U, I, users.d_pad, k, n_splits=2)
+    bias_pad, bmax, bmin = K.pack_item_bias(items.bias, I, stats, 'cuda', perm=perm, want_min=True)
+    assert np.array_equal(bmin.cpu().numpy(), bias_pad.cpu().numpy().reshape(-1, 128).min(axis=1))
+    cs, ci, theta = K.score_filter(users.split, users.scale, users.bias, unorm, hi, stats, bias_pad, bmax, perm,
+                                   U, I, users.d_pad, k, n_splits=2, block_bias_min=bmin)
     scores = oracle_scores(uf, itf, wu, wi, bu, bi)
     cs, ci = cs.cpu().numpy().reshape(U, -1), ci.cpu().numpy().reshape(U, -1)
     m = 1.5 * 2.0 ** -10 * unorm.cpu().numpy() * stats.cpu().numpy()[0] + 1e-5
     exp_i, _ = oracle.top_k_from_scores(scores, k)
-    assert int(flags.sum()) == 0
     for u in range(U):
         real = ci[u] != 2 ** 31 - 1
         assert np.all(np.abs(cs[u][real] - scores[u, ci[u][real]]) <= m[u])
@@ -474,3 +504,144 @@ def test_filter_user_block_and_kblock_shapes(K, monkeypatch, cluster, U, I, d, k
         assert np.all(np.abs(got_s - scores[rows, got_i]) <= tol[rows, got_i])
         assert (got_i != exp_i).mean() < 0.01
         assert info['fallback_rows'] <= U // 20
+
+
+# ------------------------------------------------------------------------------------------------- adversarial filter cases
+def check_float_topk(scores, tol, got_s, got_i, k):
+    U = scores.shape[0]
+    rows = np.arange(U)[:, None]
+    assert np.all(np.abs(got_s - scores[rows, got_i]) <= tol[rows, got_i])
+    mask = np.ones_like(scores, dtype=bool)
+    mask[rows, got_i] = False
+    assert np.all((scores - tol)[mask].reshape(U, -1) <= got_s[:, -1:] + 1e-6)
+    assert np.all(np.diff(got_s, axis=1) <= 0)
+
+
+def test_filter_item_bias_dominates_the_dot_products(K):
+    """|item bias| ~ 1e3 x the dot products: the admission bound, the 4-ulp bias term of m and the re-scoring all work
+    on numbers whose fp32 spacing is of the order of the dot products themselves."""
+    U, I, d, k = 300, 20000, 128, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=21, regime='indicator')
+    bi = (bi * 1e4).astype(F32)
+    model = oracle.OracleModel([wu], wi, bu, bi)
+    scores = model.predict(uf, itf)
+    tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + \
+        8 * np.spacing(np.abs(scores).astype(F32))
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k)
+    check_float_topk(scores, tol, got_s, got_i, k)
+
+
+def test_filter_norms_spanning_forty_binades(K):
+    """Row norms from 2^-20 to 2^20 on both sides: the per-row power-of-two scales differ by 2^40, the global item
+    rescale pushes small items into fp16 subnormals (flush is inside the bound), every user has its own margin."""
+    U, I, d, k = 256, 6000, 64, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=22, regime='indicator')
+    rng = np.random.default_rng(0)
+    wu = (wu * np.exp2(rng.integers(-20, 21, size=(wu.shape[0], 1)))).astype(F32)
+    wi = (wi * np.exp2(rng.integers(-20, 21, size=(wi.shape[0], 1)))).astype(F32)
+    model = oracle.OracleModel([wu], wi, None, None)
+    scores = model.predict(uf, itf)
+    ur, ir = model.user_representation(uf)[0], model.item_representation(itf)
+    # the contract is relative to |u| max_j |i_j| (the filter's error unit), rows with tiny items carry that slack
+    tol = (1e-5 * np.linalg.norm(ur, axis=1)[:, None] * np.linalg.norm(ir, axis=1).max()).astype(np.float64) + 1e-30
+    tol = np.broadcast_to(tol, scores.shape)
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, None, None, k)
+    check_float_topk(scores.astype(np.float64), tol, got_s.astype(np.float64), got_i, k)
+
+
+@pytest.mark.parametrize('cluster', ['1', '2'])
+def test_filter_all_scores_equal_at_200k_items(K, monkeypatch, cluster):
+    """Every score identical (zero weights, constant bias): the top-k is items 0..k-1 for every user, the filter can
+    certify nothing and every row goes through the device-side fallback."""
+    monkeypatch.setenv('TRK_FILTER_CLUSTER', cluster)
+    U, I, d, k = 64, 200000, 64, 12
+    uf = H.indicator_features(U, seed=1)
+    itf = H.indicator_features(I, seed=2, tags_per_row=0)      # one entry per item: every projected bias is 0.5
+    wu = np.zeros((uf.shape[1], d), F32)
+    wi = np.zeros((itf.shape[1], d), F32)
+    bu = np.zeros(uf.shape[1], F32)
+    bi = np.full(itf.shape[1], 0.5, F32)
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k)
+    scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
+    assert info['fallback_rows'] == U
+
+
+def test_filter_cluster_pairs_with_splits_and_a_ragged_last_tile(K, monkeypatch):
+    """2-CTA clusters x several item splits x an item count that leaves a 1-item last tile, U an odd number of
+    256-user groups."""
+    monkeypatch.setenv('TRK_FILTER_CLUSTER', '2')
+    for (U, I, splits, integer) in [(769, 128 * 37 + 1, 3, False), (300, 128 * 9 + 1, 4, True)]:
+        uf, itf, wu, wi, bu, bi = make_case(U, I, 128, integer, seed=U, regime='tag' if integer else 'indicator')
+        scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+        exp_i, exp_s = oracle.top_k_from_scores(scores, 10)
+        got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, 10, n_splits=splits)
+        if integer:
+            assert np.array_equal(got_i, exp_i) and np.array_equal(got_s, exp_s)
+        else:
+            model = oracle.OracleModel([wu], wi, bu, bi)
+            tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + 2e-6
+            check_float_topk(scores, tol, got_s, got_i, 10)
+            assert (got_i != exp_i).mean() < 0.01
+
+
+def test_filter_infinite_item_biases_stay_nan_free(K):
+    """-inf biases (items that must never be recommended) and a few +inf ones: no NaN reaches the result, the +inf
+    items lead every list in id order, no -inf item is returned while finite ones remain."""
+    U, I, d, k = 130, 3000, 64, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=23, regime='indicator')
+    itf = sp.csr_matrix(itf)
+    # the identity column of an item carries its own bias entry: set those directly
+    bi = bi.copy()
+    bi[:I] = 0.0
+    bi[5:I:7] = -np.inf
+    bi[[11, 400]] = np.inf
+    # tag columns keep finite biases; an item's projected bias = its identity entry + its tags
+    got_s, got_i, info = run_filter(K, uf, itf, wu, wi, bu, bi, k)
+    with np.errstate(invalid='ignore'):
+        scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+    assert not np.isnan(got_s).any()
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    assert np.array_equal(got_i[:, :2], exp_i[:, :2]) and np.all(np.isposinf(got_s[:, :2]))
+    assert not np.isneginf(got_s).any()
+    model = oracle.OracleModel([wu], wi, bu, bi)
+    tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + 2e-6
+    rows = np.arange(U)[:, None]
+    assert np.all(np.abs(got_s[:, 2:] - scores[rows, got_i[:, 2:]]) <= tol[rows, got_i[:, 2:]])
+
+
+def test_certified_and_fallback_rows_are_bit_identical_on_an_integer_fixture(K):
+    """A row's result must not depend on the route it took: re-scoring from the split operands (certified rows) and
+    the exact tensor-core kernel (rows routed through the device-side fallback) give the same bits when the arithmetic
+    is exact.  Continuous biases make the certificate pass for most rows of this integer-weight fixture; then every
+    row is forced through the fallback and the two results are compared."""
+    import torch
+    U, I, d, k = 300, 5000, 64, 10
+    uf, itf, wu, wi, bu, bi = make_case(U, I, d, True, seed=31)
+    bi = (np.arange(bi.shape[0]) % 97 * 0.125).astype(F32)         # exact in fp32, spreads the scores: few ties
+    users, items = side_operands(K, uf, wu, bu, d), side_operands(K, itf, wi, bi, d)
+    top, counters, cap = K.topk_filter(users, items, k)
+    certified = U - int(counters[0])
+    assert certified > U // 2, 'fixture should certify most rows (got %d of %d)' % (certified, U)
+    forced = K.PackedTopK(U, k, 'cuda')
+    forced.buf.zero_()
+    c2, _ = K.rerun_uncertified(users, items, torch.ones(U, dtype=torch.int32, device='cuda'), forced, k)
+    assert int(c2[0]) == U
+    assert torch.equal(top.buf, forced.buf)
+    exp_i, exp_s = oracle.top_k_from_scores(oracle_scores(uf, itf, wu, wi, bu, bi), k)
+    assert np.array_equal(top.items.cpu().numpy(), exp_i) and np.array_equal(top.scores.cpu().numpy(), exp_s)
+
+
+def test_device_side_fallback_overflow_is_reported(K):
+    """More flagged rows than the fallback buffer holds: counters[0] > capacity, nothing is written out of bounds."""
+    import torch
+    U = 5000
+    uf, itf, wu, wi, bu, bi = make_case(U, 300, 64, True, seed=33)
+    users, items = side_operands(K, uf, wu, bu, 64), side_operands(K, itf, wi, bi, 64)
+    top = K.PackedTopK(U, 5, 'cuda')
+    top.buf.fill_(-7)
+    counters, cap = K.rerun_uncertified(users, items, torch.ones(U, dtype=torch.int32, device='cuda'), top, 5)
+    assert cap == 1024 and int(counters[0]) == U
+    untouched = (top.buf == -7).all(dim=1).sum().item()
+    assert untouched == U - cap

@@ -104,6 +104,26 @@ def test_top_k_is_the_rank_le_k_set():
         assert np.array_equal(vals[u], s[u, ids[u]])
 
 
+def test_fast_top_k_equals_the_full_sort_top_k():
+    """top_k_from_scores_fast (argpartition + tie-aware ordering) == top_k_from_scores (full stable argsort), with
+    massive ties, ties straddling the k-th place, -0.0 / +0.0, infinities and k >= n_items."""
+    rng = np.random.default_rng(2)
+    for shape, k in (((9, 40), 7), ((5, 3000), 10), ((4, 12), 12), ((3, 6), 10), ((6, 500), 1)):
+        s = rng.integers(-2, 3, size=shape).astype(F32)
+        s[0, :5] = 0.0
+        s[0, 2] = -0.0
+        if shape[1] > 20:
+            s[1, 7] = np.inf
+            s[1, 9] = -np.inf
+        a_i, a_v = oracle.top_k_from_scores(s, k)
+        b_i, b_v = oracle.top_k_from_scores_fast(s, k)
+        assert np.array_equal(a_i, b_i) and np.array_equal(a_v, b_v)
+    f = rng.standard_normal((7, 2000)).astype(F32)
+    a_i, a_v = oracle.top_k_from_scores(f, 10)
+    b_i, b_v = oracle.top_k_from_scores_fast(f, 10)
+    assert np.array_equal(a_i, b_i) and np.array_equal(a_v, b_v)
+
+
 def test_spmm_duplicates_unsorted_empty_rows():
     m = H.messy_coo(37, 23, 300, seed=5)
     w = H.linear_weights(23, 12, seed=1)
