@@ -440,14 +440,16 @@ def run_b200(args):
     # sub-tolerance near-ties may order differently (fp32 rounding of the two GEMMs)
     t0 = time.perf_counter()
     rows = np.concatenate([np.arange(u_lo, u_lo + n_check), fallback_ids]).astype(np.int64)
-    exp, _, _ = oracle_topk_rows(uf, itf, wu, wi, bu, bi, rows, k)
+    emulating = world == 1 and n_shards > 1
+    exp, _, _ = oracle_topk_rows(uf, itf_local if emulating else itf, wu, wi, bu, bi, rows, k)
+    exp = exp + (lo if emulating else 0)
     got = np.concatenate([top_items_check, fallback_items]) if len(fallback_ids) else top_items_check
     agree = float((exp == got).mean()) if len(rows) else None
     same_sets = float(np.mean([set(exp[i]) == set(got[i]) for i in range(len(rows))])) if len(rows) else None
     fb_agree = float((exp[n_check:] == got[n_check:]).mean()) if len(fallback_ids) else None
     # the double-argsort oracle of the cpu_baseline leg ranks the same first users: its top-k must equal the fast oracle's
     n_dbl = min(cpu_top.shape[0], n_check)
-    oracle_self = bool(np.array_equal(cpu_top[:n_dbl], exp[:n_dbl])) if (n_dbl and u_lo == 0) else None
+    oracle_self = bool(np.array_equal(cpu_top[:n_dbl], exp[:n_dbl])) if (n_dbl and u_lo == 0 and not emulating) else None
     log('[bench] parity check on %d users in %.1fs' % (len(rows), time.perf_counter() - t0))
 
     def phase_table(col):

@@ -67,6 +67,15 @@ int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const f
                               int32_t n_normalize, float* out_f32, void* out_split, int32_t d_pad,
                               float* out_scale, float* out_norm, float* stats, void* stream);
 
+/* L2 residency for K1's re-referenced weight rows.  In the indicator regime (tensorrec/util.py:88-117) every feature
+ * row reads its own identity weight row once (pure streaming) plus a few rows of a much smaller tag table that all rows
+ * share; next to ~2 GB of streaming traffic the tag rows are evicted between uses and re-read from HBM.
+ * trk_l2_persist_window marks [base, base + bytes) as PERSISTING for kernels launched on `stream` afterwards (CUDA
+ * access-policy window; everything else on the stream becomes streaming), clamped to the device's carve-out;
+ * bytes = 0 clears the window and resets the persisting lines.  trk_l2_persist_capacity: the carve-out in bytes. */
+int trk_l2_persist_window(const void* base, size_t bytes, float hit_ratio, void* stream);
+int64_t trk_l2_persist_capacity(void);
+
 /* Converts an existing dense fp32 representation [rows, d] into the split-fp16 operand + scales
  * (same layout as above).  Used when a representation comes from a user-defined plugin graph. */
 int trk_split_f32_to_f16x2(const float* repr, int64_t rows, int32_t d, int32_t n_normalize, void* out_split,
@@ -209,16 +218,20 @@ int trk_rescore_topk_split(const void* user_split, const float* user_scale, cons
 
 /* Device-side routing of the flagged users (no host round trip):
  *   trk_select_flagged_rows  idx[0 .. min(count, capacity)) = rows with flags != 0 (any order), counters[0] = count
- *                            (counters: int32[2], zeroed by this call; count > capacity = overflow, the host layer
+ *                            (counters: int32[4], zeroed by this call; count > capacity = overflow, the host layer
  *                            checks it at its next natural synchronisation and re-runs the whole batch exactly);
  *   trk_gather_operand_rows  sub_split / sub_scale / sub_bias [capacity, ...] = the selected rows of a split operand;
- *   trk_score_topk_f16x3 + trk_topk_merge with n_users_live = counters re-score exactly those rows;
+ *                            also sets the live counts of the two re-scoring tiers: counters[2] = count when
+ *                            count <= small_capacity (else 0), counters[3] = min(count, capacity) otherwise (else 0);
+ *   trk_score_topk_f16x3 + trk_topk_merge with n_users_live = &counters[2] over the first small_capacity rows and MANY
+ *                            item splits (a handful of user blocks still fills the machine), and with n_users_live =
+ *                            &counters[3] over all capacity rows and few splits: exactly one tier does work;
  *   trk_scatter_topk_rows    out[idx[i]] = sub[i] for i < min(count, capacity) (row i of sub_* at i * sub_row_stride). */
 int trk_select_flagged_rows(const int32_t* flags, int64_t n, int32_t* idx, int32_t capacity, int32_t* counters,
                             void* stream);
-int trk_gather_operand_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const void* split,
-                            const float* scale, const float* bias, int32_t d_pad, void* sub_split, float* sub_scale,
-                            float* sub_bias, void* stream);
+int trk_gather_operand_rows(const int32_t* idx, int32_t* counters, int32_t capacity, int32_t small_capacity,
+                            const void* split, const float* scale, const float* bias, int32_t d_pad, void* sub_split,
+                            float* sub_scale, float* sub_bias, void* stream);
 int trk_scatter_topk_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const float* sub_score,
                           const int32_t* sub_item, int64_t sub_row_stride, int32_t k, float* out_score,
                           int32_t* out_item, int64_t out_row_stride, void* stream);

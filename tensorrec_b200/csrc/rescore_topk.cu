@@ -151,12 +151,20 @@ __global__ void select_flagged_rows_kernel(const int32_t* __restrict__ flags, in
   }
 }
 
-// sub_*[i] = *[idx[i]] for i < min(count, capacity): split rows (2 d_pad halves), scale, bias
-__global__ void gather_operand_rows_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ counters,
-                                           int capacity, const uint4* __restrict__ split, const float* __restrict__ scale,
-                                           const float* __restrict__ bias, int row_vec, uint4* __restrict__ sub_split,
-                                           float* __restrict__ sub_scale, float* __restrict__ sub_bias) {
+// sub_*[i] = *[idx[i]] for i < min(count, capacity): split rows (2 d_pad halves), scale, bias.  Also publishes the live
+// row counts of the two re-scoring tiers: counters[2] = count if it fits the small tier (few rows: the exact kernel is
+// then launched with many item splits so that a handful of user blocks still fills the machine), else 0;
+// counters[3] = min(count, capacity) if it does not, else 0.
+__global__ void gather_operand_rows_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ counters,
+                                           int capacity, int small_capacity, const uint4* __restrict__ split,
+                                           const float* __restrict__ scale, const float* __restrict__ bias, int row_vec,
+                                           uint4* __restrict__ sub_split, float* __restrict__ sub_scale,
+                                           float* __restrict__ sub_bias) {
   const int n = min(counters[0], capacity);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[2] = counters[0] <= small_capacity ? counters[0] : 0;
+    counters[3] = counters[0] <= small_capacity ? 0 : n;
+  }
   const int lane = threadIdx.x % 32;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * blockDim.x / 32;
@@ -265,7 +273,7 @@ int rescore_topk(const void* user_split, const float* user_scale, const void* it
 int select_flagged_rows(const int32_t* flags, int64_t n, int32_t* idx, int32_t capacity, int32_t* counters,
                         cudaStream_t stream) {
   TRK_CHECK_ARG(flags && idx && counters && n >= 0 && capacity >= 1, "select_flagged_rows: bad arguments");
-  TRK_CHECK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), stream));
+  TRK_CHECK_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int32_t), stream));
   if (n == 0) return TRK_OK;
   const int threads = 256;
   const int64_t blocks = ceil_div(n, threads);
@@ -276,9 +284,9 @@ int select_flagged_rows(const int32_t* flags, int64_t n, int32_t* idx, int32_t c
   return TRK_OK;
 }
 
-int gather_operand_rows(const int32_t* idx, const int32_t* counters, int32_t capacity, const void* split,
-                        const float* scale, const float* bias, int32_t d_pad, void* sub_split, float* sub_scale,
-                        float* sub_bias, cudaStream_t stream) {
+int gather_operand_rows(const int32_t* idx, int32_t* counters, int32_t capacity, int32_t small_capacity,
+                        const void* split, const float* scale, const float* bias, int32_t d_pad, void* sub_split,
+                        float* sub_scale, float* sub_bias, cudaStream_t stream) {
   TRK_CHECK_ARG(idx && counters && split && scale && sub_split && sub_scale && capacity >= 1 && d_pad >= 64 &&
                     d_pad % 64 == 0,
                 "gather_operand_rows: bad arguments");
@@ -287,7 +295,7 @@ int gather_operand_rows(const int32_t* idx, const int32_t* counters, int32_t cap
   const int64_t blocks = ceil_div(static_cast<int64_t>(capacity), threads / 32);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   gather_operand_rows_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), threads, 0, stream>>>(
-      idx, counters, capacity, static_cast<const uint4*>(split), scale, bias, 2 * d_pad * 2 / 16,
+      idx, counters, capacity, small_capacity, static_cast<const uint4*>(split), scale, bias, 2 * d_pad * 2 / 16,
       static_cast<uint4*>(sub_split), sub_scale, sub_bias);
   TRK_CHECK_LAUNCH();
   return TRK_OK;

@@ -571,29 +571,46 @@ def fallback_capacity(n_users):
     return ((cap + 127) // 128) * 128
 
 
+FALLBACK_SMALL_ROWS = 1024     # the small re-scoring tier: at most this many flagged rows, many item splits
+
+
+def _ptr_at(t, index):
+    return ctypes.c_void_p(t.data_ptr() + index * t.element_size())
+
+
 def rerun_uncertified(users, items, bad, top, k, item_id_offset=0):
     """Users flagged by the certificate go through the exact kernel WITHOUT a host round trip: the flagged rows are
     compacted on the device, their operands gathered into a fixed-capacity buffer, the exact kernel runs over that buffer
-    with the device-side count and the rows are scattered back into `top`.  Returns counters (device int32[2]):
-    [0] = flagged rows; > capacity means overflow (the caller checks it at its next synchronisation)."""
+    with the device-side count and the rows are scattered back into `top`.  Two tiers are launched, exactly one does
+    work (decided on the device): up to FALLBACK_SMALL_ROWS rows (the normal case: ~0.01 % of the users) with as many
+    item splits as it takes to fill the machine from one or two user blocks, or up to `capacity` rows with few splits.
+    Returns (counters, capacity); counters[0] = flagged rows, > capacity means overflow (the caller checks it at its
+    next synchronisation)."""
     lib = require_cuda()
     dev = users.split.device
     cap = fallback_capacity(users.n_rows)
+    small = min(cap, FALLBACK_SMALL_ROWS)
     idx = torch.empty((cap,), dtype=torch.int32, device=dev)
-    counters = torch.empty((2,), dtype=torch.int32, device=dev)
+    counters = torch.empty((4,), dtype=torch.int32, device=dev)
     rc = lib.trk_select_flagged_rows(_p(bad), users.n_rows, _p(idx), cap, _p(counters), _stream())
     _lib.check(rc, 'trk_select_flagged_rows')
     sub_split = torch.empty((cap, 2 * users.d_pad), dtype=torch.float16, device=dev)
     sub_scale = torch.empty((cap,), dtype=torch.float32, device=dev)
     sub_bias = None if users.bias is None else torch.empty((cap,), dtype=torch.float32, device=dev)
-    rc = lib.trk_gather_operand_rows(_p(idx), _p(counters), cap, _p(users.split), _p(users.scale), _p(users.bias),
-                                     int(users.d_pad), _p(sub_split), _p(sub_scale), _p(sub_bias), _stream())
+    rc = lib.trk_gather_operand_rows(_p(idx), _p(counters), cap, small, _p(users.split), _p(users.scale),
+                                     _p(users.bias), int(users.d_pad), _p(sub_split), _p(sub_scale), _p(sub_bias),
+                                     _stream())
     _lib.check(rc, 'trk_gather_operand_rows')
     sub = SideOperands(None, sub_split, sub_scale, sub_bias, cap, users.d, users.d_pad)
-    exact = topk_exact(sub, items, k, item_id_offset=item_id_offset, n_users_live=counters)
-    rc = lib.trk_scatter_topk_rows(_p(idx), _p(counters), cap, exact.score_ptr(), exact.item_ptr(), 2 * exact.k, int(k),
-                                   top.score_ptr(), top.item_ptr(), 2 * top.k, _stream())
-    _lib.check(rc, 'trk_scatter_topk_rows')
+    tiers = [(sub.rows(0, small), small, 2, default_splits(2 * TILE_USERS, items.n_rows))]
+    if cap > small:
+        tiers.append((sub, cap, 3, None))
+    for tier_rows, n_rows, slot, n_splits in tiers:
+        live = counters[slot:slot + 1]
+        exact = topk_exact(tier_rows, items, k, n_splits=n_splits, item_id_offset=item_id_offset, n_users_live=live)
+        rc = lib.trk_scatter_topk_rows(_p(idx), _ptr_at(counters, slot), n_rows, exact.score_ptr(), exact.item_ptr(),
+                                       2 * exact.k, int(k), top.score_ptr(), top.item_ptr(), 2 * top.k, _stream())
+        _lib.check(rc, 'trk_scatter_topk_rows')
     return counters, cap
 
 

@@ -634,7 +634,8 @@ def test_certified_and_fallback_rows_are_bit_identical_on_an_integer_fixture(K):
 
 
 def test_device_side_fallback_overflow_is_reported(K):
-    """More flagged rows than the fallback buffer holds: counters[0] > capacity, nothing is written out of bounds."""
+    """More flagged rows than the fallback buffer holds: counters[0] > capacity tells the host layer to re-run the batch
+    through the exact kernel; the device-side tiers then do no work and nothing is written out of bounds."""
     import torch
     U = 5000
     uf, itf, wu, wi, bu, bi = make_case(U, 300, 64, True, seed=33)
@@ -643,5 +644,26 @@ def test_device_side_fallback_overflow_is_reported(K):
     top.buf.fill_(-7)
     counters, cap = K.rerun_uncertified(users, items, torch.ones(U, dtype=torch.int32, device='cuda'), top, 5)
     assert cap == 1024 and int(counters[0]) == U
-    untouched = (top.buf == -7).all(dim=1).sum().item()
-    assert untouched == U - cap
+    assert bool((top.buf == -7).all())
+
+
+def test_device_side_fallback_large_tier(K, monkeypatch):
+    """More flagged rows than the small tier holds but fewer than the capacity: the large tier re-scores them."""
+    import torch
+    monkeypatch.setattr(K, 'FALLBACK_SMALL_ROWS', 128)
+    U, I, k = 1500, 700, 5
+    uf, itf, wu, wi, bu, bi = make_case(U, I, 64, True, seed=34)
+    users, items = side_operands(K, uf, wu, bu, 64), side_operands(K, itf, wi, bi, 64)
+    exp_i, exp_s = oracle.top_k_from_scores(oracle_scores(uf, itf, wu, wi, bu, bi), k)
+    flags = torch.zeros(U, dtype=torch.int32, device='cuda')
+    chosen = np.arange(0, U, 3)                                  # 500 rows: > 128, < capacity (1024)
+    flags[torch.from_numpy(chosen).cuda()] = 1
+    top = K.PackedTopK(U, k, 'cuda')
+    top.buf.fill_(-7)
+    counters, cap = K.rerun_uncertified(users, items, flags, top, k)
+    c = counters.cpu().numpy()
+    assert c[0] == len(chosen) and c[2] == 0 and c[3] == len(chosen)
+    got_i, got_s = top.items.cpu().numpy(), top.scores.cpu().numpy()
+    assert np.array_equal(got_i[chosen], exp_i[chosen]) and np.array_equal(got_s[chosen], exp_s[chosen])
+    rest = np.setdiff1d(np.arange(U), chosen)
+    assert np.all(top.buf.cpu().numpy()[rest] == -7)
