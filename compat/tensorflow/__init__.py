@@ -12,7 +12,7 @@ aliases the reference's (numpy-1 era) tests use: np.mat, np.int."""
 import numpy as np
 import torch
 
-from tensorrec_b200.session_management import get_variable
+from tensorrec_b200.session_management import get_variable, next_anonymous_name
 
 Tensor = torch.Tensor
 float32, int64, int32 = torch.float32, torch.int64, torch.int32
@@ -56,15 +56,12 @@ def SparseTensor(indices, values, dense_shape):
                                    check_invariants=False)
 
 
-_anonymous_variables = [0]
-
-
 def Variable(initial_value, name=None, dtype=None, trainable=True):
     """tf.Variable: a trainable tensor registered under its name in the model's variable scope (created once, like a
-    graph variable; plugin methods run on every training step)."""
+    graph variable; plugin methods run on every training step).  An unnamed variable gets a name that is stable across
+    steps: 'Variable_<plugin call>_<n-th anonymous variable of that call>' (session_management.name_scope)."""
     if name is None:
-        _anonymous_variables[0] += 1
-        name = 'Variable_%d' % _anonymous_variables[0]
+        name = next_anonymous_name()
     return get_variable(name, lambda: _t(initial_value).to(torch.float32))
 
 

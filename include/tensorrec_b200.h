@@ -67,15 +67,6 @@ int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const f
                               int32_t n_normalize, float* out_f32, void* out_split, int32_t d_pad,
                               float* out_scale, float* out_norm, float* stats, void* stream);
 
-/* L2 residency for K1's re-referenced weight rows.  In the indicator regime (tensorrec/util.py:88-117) every feature
- * row reads its own identity weight row once (pure streaming) plus a few rows of a much smaller tag table that all rows
- * share; next to ~2 GB of streaming traffic the tag rows are evicted between uses and re-read from HBM.
- * trk_l2_persist_window marks [base, base + bytes) as PERSISTING for kernels launched on `stream` afterwards (CUDA
- * access-policy window; everything else on the stream becomes streaming), clamped to the device's carve-out;
- * bytes = 0 clears the window and resets the persisting lines.  trk_l2_persist_capacity: the carve-out in bytes. */
-int trk_l2_persist_window(const void* base, size_t bytes, float hit_ratio, void* stream);
-int64_t trk_l2_persist_capacity(void);
-
 /* Converts an existing dense fp32 representation [rows, d] into the split-fp16 operand + scales
  * (same layout as above).  Used when a representation comes from a user-defined plugin graph. */
 int trk_split_f32_to_f16x2(const float* repr, int64_t rows, int32_t d, int32_t n_normalize, void* out_split,

@@ -1,7 +1,6 @@
 """K1 (csr_gather_reduce) timing at the bench shape (L2 flushed between launches): output variants, and with the
 re-referenced tag rows of the indicator regime pinned in L2 (trk_l2_persist_window).
 usage: python scripts/k1_probe.py [rows]"""
-import ctypes
 import os
 import sys
 
@@ -10,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from tensorrec_b200 import kernels, _lib  # noqa: E402
+from tensorrec_b200 import kernels  # noqa: E402
 
 
 class A:
@@ -25,7 +24,6 @@ w = torch.from_numpy(wu).to(dev)
 bu_d = torch.from_numpy(bu).to(dev)
 d_pad = kernels.d_pad_for(A.d)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-lib = _lib.load()
 
 
 def timeit(fn, n=7):
@@ -45,8 +43,7 @@ def timeit(fn, n=7):
 nnz = uf.nnz
 distinct = int(np.unique(uf.indices).shape[0])
 survey = nnz * 8 + (A.users + 1) * 4 + distinct * A.d * 4 + A.users * A.d * 4
-print('%d rows, nnz %d, distinct columns %d, SURVEY 8(d) bytes %.3f GB, persisting L2 capacity %.1f MB'
-      % (A.users, nnz, distinct, survey / 1e9, lib.trk_l2_persist_capacity() / 1e6))
+print('indicator regime: %d rows, nnz %d, distinct columns %d, SURVEY 8(d) bytes %.3f GB' % (A.users, nnz, distinct, survey / 1e9))
 
 
 def report(name, ms):
@@ -61,15 +58,13 @@ variants = [('split only', dict(want_f32=False, split_d_pad=d_pad)),
 for name, kw in variants:
     report('K1 ' + name, timeit(lambda: kernels.gather_reduce(ucsr, w, **kw)))
 report('project_biases', timeit(lambda: kernels.project_biases(ucsr, bu_d)))
-# the tag table of the indicator regime = weight rows [users, 1.2 users): pin it
-stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-tag_base = w.data_ptr() + A.users * A.d * 4
-tag_bytes = (w.shape[0] - A.users) * A.d * 4
-for ratio in (1.0, 0.6):
-    rc = lib.trk_l2_persist_window(ctypes.c_void_p(tag_base), tag_bytes, ctypes.c_float(ratio), stream)
-    print('persist window over the tag rows (%.0f MB, hit ratio %.1f): rc=%d %s' % (tag_bytes / 1e6, ratio, rc,
-                                                                                    _lib.last_error() if rc else ''))
-    for name, kw in variants[:2]:
-        report('K1 ' + name + ' [tag rows persisting]', timeit(lambda: kernels.gather_reduce(ucsr, w, **kw)))
-lib.trk_l2_persist_window(None, 0, ctypes.c_float(0.0), stream)
-report('K1 split only [window cleared]', timeit(lambda: kernels.gather_reduce(ucsr, w, want_f32=False, split_d_pad=d_pad)))
+# tag regime (tensorrec/util.py:61-85: 200 features, ~20 nnz per row): the 100 KB table lives in L2, the kernel is bound by
+# the index stream and the output write -- SURVEY 8(d): 20*8 + 4 + 512 = 676 B per row
+from tests import helpers as H  # noqa: E402
+tf = H.tag_features(A.users, 200, 20, seed=0)
+tcsr = kernels.DeviceCSR.from_scipy(tf, device=dev)
+tw = torch.from_numpy(H.linear_weights(200, A.d, seed=2)).to(dev)
+survey = tf.nnz * 8 + (A.users + 1) * 4 + 200 * A.d * 4 + A.users * A.d * 4
+print('tag regime: %d rows, nnz %d, SURVEY 8(d) bytes %.3f GB' % (A.users, tf.nnz, survey / 1e9))
+for name, kw in variants[:3]:
+    report('K1 tag regime, ' + name, timeit(lambda: kernels.gather_reduce(tcsr, tw, **kw)))

@@ -27,8 +27,6 @@ SIGNATURES = {
     'trk_last_error': (ctypes.c_char_p, []),
     'trk_csr_gather_reduce_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i32, _c_i32, _c_i32, _c_p, _c_p,
                                                  _c_i32, _c_p, _c_p, _c_p, _c_p]),
-    'trk_l2_persist_window': (ctypes.c_int, [_c_p, _c_sz, ctypes.c_float, _c_p]),
-    'trk_l2_persist_capacity': (_c_i64, []),
     'trk_split_f32_to_f16x2': (ctypes.c_int, [_c_p, _c_i64, _c_i32, _c_i32, _c_p, _c_i32, _c_p, _c_p]),
     'trk_l2_normalize_rows_f32': (ctypes.c_int, [_c_p, _c_i64, _c_i32, _c_p]),
     'trk_csr_project_biases_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p]),

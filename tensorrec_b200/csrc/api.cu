@@ -70,43 +70,6 @@ extern "C" {
 
 int trk_version(void) { return 2000; }
 
-int trk_l2_persist_window(const void* base, size_t bytes, float hit_ratio, void* stream) {
-  // bytes == 0 clears the window of the stream and releases the persisting lines
-  cudaStreamAttrValue attr;
-  memset(&attr, 0, sizeof(attr));
-  if (bytes == 0 || base == nullptr) {
-    attr.accessPolicyWindow.num_bytes = 0;
-    TRK_CHECK_CUDA(cudaStreamSetAttribute(trk::as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr));
-    TRK_CHECK_CUDA(cudaCtxResetPersistingL2Cache());
-    return TRK_OK;
-  }
-  int dev = 0, max_persist = 0, max_window = 0;
-  TRK_CHECK_CUDA(cudaGetDevice(&dev));
-  TRK_CHECK_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-  TRK_CHECK_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-  TRK_CHECK_ARG(max_persist > 0 && max_window > 0, "trk_l2_persist_window: the device has no persisting L2 carve-out");
-  TRK_CHECK_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist)));
-  if (bytes > static_cast<size_t>(max_window)) bytes = static_cast<size_t>(max_window);
-  attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-  attr.accessPolicyWindow.num_bytes = bytes;
-  // lines of the window beyond what the carve-out holds would evict each other: let only that fraction persist
-  float ratio = hit_ratio;
-  if (static_cast<double>(bytes) * ratio > static_cast<double>(max_persist))
-    ratio = static_cast<float>(static_cast<double>(max_persist) / static_cast<double>(bytes));
-  attr.accessPolicyWindow.hitRatio = ratio;
-  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  TRK_CHECK_CUDA(cudaStreamSetAttribute(trk::as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr));
-  return TRK_OK;
-}
-
-int64_t trk_l2_persist_capacity(void) {
-  int dev = 0, max_persist = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess) return 0;
-  return max_persist;
-}
-
 const char* trk_last_error(void) { return trk::g_last_error; }
 
 int trk_csr_gather_reduce_f32(const int32_t* indptr, const int32_t* col, const float* val, const float* weights,

@@ -62,6 +62,26 @@ def variable_scope(store):
 
 
 @contextlib.contextmanager
+def name_scope(label):
+    """Names the plugin call that is about to run ('item', 'user_0', 'attn_1', 'loss', ...).  Variables a plugin creates
+    WITHOUT a name (tf.Variable(initial_value) in code written against the reference) are registered as
+    'Variable_<label>_<n>', n counting the anonymous creations inside this call: the same call creates the same names
+    on every training step and at predict time, whatever ran before it (the reference gets this from building its graph
+    once; define-by-run code re-runs the plugin methods every step)."""
+    previous = getattr(_scope, 'label', None), getattr(_scope, 'anonymous', 0)
+    _scope.label, _scope.anonymous = str(label), 0
+    try:
+        yield
+    finally:
+        _scope.label, _scope.anonymous = previous
+
+
+def next_anonymous_name():
+    _scope.anonymous = getattr(_scope, 'anonymous', 0) + 1
+    return 'Variable_{}_{}'.format(getattr(_scope, 'label', None) or 'anonymous', _scope.anonymous)
+
+
+@contextlib.contextmanager
 def training_step():
     """Inside a training step every graph function evaluates with differentiable torch ops, also when no input
     happens to carry a gradient (weight-free representation graphs): the kernel path is the predict path."""

@@ -38,7 +38,7 @@ from .recommendation_graphs import (
 from .representation_graphs import (
     AbstractRepresentationGraph, LinearRepresentationGraph, NormalizedLinearRepresentationGraph
 )
-from .session_management import get_session, variable_scope, get_variable
+from .session_management import get_session, variable_scope, get_variable, name_scope
 from .util import sample_items, calculate_batched_alpha
 
 TopK = collections.namedtuple('TopK', ['items', 'scores'])
@@ -53,6 +53,15 @@ SCORE_PATH = os.environ.get('TENSORREC_B200_SCORE_PATH', 'auto')
 # predict_rank(k) on the tensor path: 'auto' = 1-pass filter + exact fp32 re-scoring when k allows, 'exact' = always the
 # 3-pass split-product kernel
 TOPK_PATH = os.environ.get('TENSORREC_B200_TOPK_PATH', 'auto')
+
+
+def _names_argument(method, name):
+    """Does `method` declare `name` as an explicit parameter (not just **kwargs)?"""
+    import inspect
+    try:
+        return name in inspect.signature(method).parameters
+    except (TypeError, ValueError):
+        return True
 
 
 class _Hook(object):
@@ -130,6 +139,7 @@ class TensorRec(object):
         self._variables = collections.OrderedDict()   # name -> trainable tensor (the model's weights)
         self._optimizer = None
         self._optimizer_params = None
+        self._stepped = False          # has any training step completed?
 
     # ------------------------------------------------------------------------------------------------
     # graph hooks (tensorrec.py:136-183).  Only their None-ness carries meaning here.
@@ -222,9 +232,10 @@ class TensorRec(object):
         loss_graph = self.loss_graph_factory
         tf_weights = []
 
-        item_repr, item_weights = self.item_repr_graph_factory.connect_representation_graph(
-            tf_features=tf_item_features, n_components=self.n_components, n_features=self.n_item_features,
-            node_name_ending='item')
+        with name_scope('item'):
+            item_repr, item_weights = self.item_repr_graph_factory.connect_representation_graph(
+                tf_features=tf_item_features, n_components=self.n_components, n_features=self.n_item_features,
+                node_name_ending='item')
         tf_weights.extend(item_weights)
 
         tf_x_user, tf_x_item = split_sparse_tensor_indices(tf_sparse_tensor=tf_interactions, n_dimensions=2)
@@ -241,15 +252,17 @@ class TensorRec(object):
         tastes_sample_attention_serials = [] if with_attention else None
 
         for taste in range(self.n_tastes):
-            user_repr, user_weights = self.user_repr_graph_factory.connect_representation_graph(
-                tf_features=tf_user_features, n_components=self.n_components, n_features=self.n_user_features,
-                node_name_ending='user_{}'.format(taste))
+            with name_scope('user_{}'.format(taste)):
+                user_repr, user_weights = self.user_repr_graph_factory.connect_representation_graph(
+                    tf_features=tf_user_features, n_components=self.n_components, n_features=self.n_user_features,
+                    node_name_ending='user_{}'.format(taste))
             tf_weights.extend(user_weights)
 
             if with_attention:
-                attention_repr, attention_weights = self.attention_graph_factory.connect_representation_graph(
-                    tf_features=tf_user_features, n_components=self.n_components, n_features=self.n_user_features,
-                    node_name_ending='attn_{}'.format(taste))
+                with name_scope('attn_{}'.format(taste)):
+                    attention_repr, attention_weights = self.attention_graph_factory.connect_representation_graph(
+                        tf_features=tf_user_features, n_components=self.n_components,
+                        n_features=self.n_user_features, node_name_ending='attn_{}'.format(taste))
                 tf_weights.extend(attention_weights)
                 if loss_graph.is_dense:
                     tastes_attentions.append(pred_graph.connect_dense_prediction_graph(
@@ -310,8 +323,11 @@ class TensorRec(object):
             'tf_n_items': n_items,
         }
         if loss_graph.is_dense:
+            # In the reference tf_rankings is a graph node that costs nothing unless the loss graph consumes it; here it
+            # is a full K3 sort of [n_users, n_items] per step, so it is evaluated only for a loss graph that names it
             tf_rankings = None
-            if tf_prediction.is_cuda:   # ranks come from the K3 kernel; they carry no gradient (as tf.nn.top_k)
+            if tf_prediction.is_cuda and _names_argument(loss_graph.connect_loss_graph, 'tf_rankings'):
+                # ranks come from the K3 kernel; they carry no gradient (as tf.nn.top_k)
                 tf_rankings = kernels.rank_full(tf_prediction.detach().contiguous())
             loss_graph_kwargs.update({'tf_prediction': tf_prediction, 'tf_rankings': tf_rankings})
         if loss_graph.is_sample_based:
@@ -321,7 +337,8 @@ class TensorRec(object):
                     tf_n_sampled_items=n_sampled_items, tf_n_users=n_users),
                 'tf_n_sampled_items': n_sampled_items})
 
-        basic_loss = loss_graph.connect_loss_graph(**loss_graph_kwargs)
+        with name_scope('loss'):
+            basic_loss = loss_graph.connect_loss_graph(**loss_graph_kwargs)
         weight_reg_loss = sum(0.5 * torch.sum(w * w) for w in tf_weights)      # sum of tf.nn.l2_loss
         return basic_loss, weight_reg_loss, tf_prediction_serial, tf_weights
 
@@ -348,7 +365,8 @@ class TensorRec(object):
         batches = self._create_batched_inputs(interactions=interactions, user_features=user_features,
                                               item_features=item_features, user_batch_size=user_batch_size)
 
-        if self.tf_prediction is None:
+        first_build = self.tf_prediction is None
+        if first_build:
             # feature counts are learned from the first batch and cannot change afterwards (tensorrec.py:598-605)
             self.n_user_features = batches[0][1].shape[1]
             self.n_item_features = batches[0][2].shape[1]
@@ -357,7 +375,19 @@ class TensorRec(object):
         batched_alpha = calculate_batched_alpha(num_batches=len(batches), alpha=alpha)
         if verbose:
             logging.info('Beginning fitting')
+        try:
+            self._fit_epochs(batches, epochs, learning_rate, alpha, batched_alpha, verbose, n_sampled_items, device)
+            first_build = False
+        finally:
+            if first_build and not getattr(self, '_stepped', False):
+                # the very first step failed (e.g. n_sampled_items > n_items): the model is still unbuilt -- predict()
+                # must keep raising ModelNotFitException and a later fit may use other feature counts
+                self._break_graph_hooks()
+                self.n_user_features = self.n_item_features = None
+                self._variables.clear()
+                self._optimizer = None
 
+    def _fit_epochs(self, batches, epochs, learning_rate, alpha, batched_alpha, verbose, n_sampled_items, device):
         for epoch in range(epochs):
             for batch, (int_in, uf_in, if_in) in enumerate(batches):
                 if uf_in.shape[1] != self.n_user_features or if_in.shape[1] != self.n_item_features:
@@ -372,6 +402,7 @@ class TensorRec(object):
                 self._optimizer.zero_grad(set_to_none=True)
                 loss.sum().backward()       # tf.gradients of a vector loss (WMRB) is the gradient of its sum
                 self._optimizer.step()
+                self._stepped = True
                 if verbose:
                     mean_loss = float(torch.mean(basic_loss.detach()))
                     mean_pred = float(torch.mean(serial_predictions.detach()))
@@ -444,7 +475,7 @@ class TensorRec(object):
             return kernels.gather_reduce(sparse_input.device_csr(device), weights, n_normalize=n_norm,
                                          want_f32=want_f32, split_d_pad=split_d_pad, want_norm=want_norm, stats=stats)
         # user-defined / non-linear plugin: run its own forward on the device, then hand the dense rows to the kernels
-        with torch.no_grad(), variable_scope(self._variables):
+        with torch.no_grad(), variable_scope(self._variables), name_scope(node_name_ending):
             for k in list(self._variables):
                 self._var(k, device)
             dense, _ = graph.connect_representation_graph(
@@ -502,6 +533,63 @@ class TensorRec(object):
     def _tensor_operands(self, user_in, item_in, device):
         return self._side_operands('user', user_in, device), self._side_operands('item', item_in, device)
 
+    def _score_plan(self, item_in, device):
+        """Item-side work of the dense prediction, done once per call: returns score(user_block_in, out=None) ->
+        float32 [rows, n_items] on the device.  Tensor cores (split-product kernel) when the model allows, the exact
+        CUDA-core kernel (tastes, attention, Euclidean, wide rows) or the plugin's own dense form otherwise."""
+        n_items = item_in.shape[0]
+        if self._tensor_path_ok():
+            items = self._side_operands('item', item_in, device)
+            meta = kernels.pack_item_meta(items.scale, items.bias, n_items)
+
+            def score(block_in, out=None):
+                users = self._side_operands('user', block_in, device)
+                return kernels.score_dense_tc(users.split, users.scale, users.bias, items.split, meta,
+                                              block_in.shape[0], n_items, users.d_pad, out=out)
+            return score
+
+        pred_graph = self.prediction_graph_factory
+        builtin = type(pred_graph) in _BUILTIN_PRED
+        extra = 1 if (builtin and pred_graph.b200_kind == 'cosine') else 0
+        item_repr, _, _ = self._represent(self.item_repr_graph_factory, item_in, self.n_item_features, 'item', device,
+                                          extra)
+        item_bias = self._projected_biases(item_in, 'feature_biases_item', device) if self.biased else None
+
+        def score(block_in, out=None):
+            user_reprs = torch.stack([self._represent(self.user_repr_graph_factory, block_in, self.n_user_features,
+                                                      'user_{}'.format(t), device, extra)[0]
+                                      for t in range(self.n_tastes)])
+            attention_reprs = None
+            if self.attention_graph_factory is not None:
+                attention_reprs = torch.stack([self._represent(self.attention_graph_factory, block_in,
+                                                               self.n_user_features, 'attn_{}'.format(t), device,
+                                                               extra)[0]
+                                               for t in range(self.n_tastes)])
+            user_bias = self._projected_biases(block_in, 'feature_biases_user', device) if self.biased else None
+            if builtin and not (pred_graph.b200_kind == 'euclidean' and attention_reprs is not None):
+                mode = 1 if pred_graph.b200_kind == 'euclidean' else 0
+                return kernels.score_exact(user_reprs, item_repr, user_bias, item_bias, mode=mode,
+                                           attention_repr=attention_reprs, out=out)
+            # user-defined prediction graph: its own dense form per taste, then the reference's collapse + bias order
+            with torch.no_grad():
+                preds = [pred_graph.connect_dense_prediction_graph(tf_user_representation=user_reprs[t],
+                                                                   tf_item_representation=item_repr)
+                         for t in range(self.n_tastes)]
+                atts = None
+                if attention_reprs is not None:
+                    atts = [pred_graph.connect_dense_prediction_graph(tf_user_representation=attention_reprs[t],
+                                                                      tf_item_representation=item_repr)
+                            for t in range(self.n_tastes)]
+                pred = collapse_mixture_of_tastes(preds, atts)
+                if self.biased:
+                    pred = bias_prediction_dense(pred, user_bias, item_bias)
+            pred = pred.to(torch.float32).contiguous()
+            if out is not None:
+                out.copy_(pred)
+                return out
+            return pred
+        return score
+
     def _predict_device(self, user_in, item_in, device):
         """tf_prediction: dense float32 scores [n_users, n_items] on the device."""
         self._check_features(user_in, self.n_user_features, 'user')
@@ -509,57 +597,104 @@ class TensorRec(object):
         n_users, n_items = user_in.shape[0], item_in.shape[0]
         if n_users == 0 or n_items == 0:
             return torch.zeros((n_users, n_items), dtype=torch.float32, device=device)
-        if self._tensor_path_ok():
-            users, items = self._tensor_operands(user_in, item_in, device)
-            meta = kernels.pack_item_meta(items.scale, items.bias, n_items)
-            return kernels.score_dense_tc(users.split, users.scale, users.bias, items.split, meta, n_users, n_items,
-                                          users.d_pad)
+        return self._score_plan(item_in, device)(user_in)
 
-        pred_graph = self.prediction_graph_factory
-        builtin = type(pred_graph) in _BUILTIN_PRED
-        extra = 1 if (builtin and pred_graph.b200_kind == 'cosine') else 0
-        item_repr, _, _ = self._represent(self.item_repr_graph_factory, item_in, self.n_item_features, 'item', device,
-                                          extra)
-        user_reprs = torch.stack([self._represent(self.user_repr_graph_factory, user_in, self.n_user_features,
-                                                  'user_{}'.format(t), device, extra)[0]
-                                  for t in range(self.n_tastes)])
-        attention_reprs = None
-        if self.attention_graph_factory is not None:
-            attention_reprs = torch.stack([self._represent(self.attention_graph_factory, user_in, self.n_user_features,
-                                                           'attn_{}'.format(t), device, extra)[0]
-                                           for t in range(self.n_tastes)])
-        user_bias = item_bias = None
-        if self.biased:
-            user_bias = self._projected_biases(user_in, 'feature_biases_user', device)
-            item_bias = self._projected_biases(item_in, 'feature_biases_item', device)
+    # a dense [n_users, n_items] result beyond this many bytes is produced in user blocks (BASELINE config #2,
+    # 1M x 100K = 400 GB, exceeds the 180 GB of HBM): two device buffers + two page-locked host buffers of this size
+    PREDICT_BLOCK_BYTES = 4 << 30
 
-        if builtin and not (pred_graph.b200_kind == 'euclidean' and attention_reprs is not None):
-            mode = 1 if pred_graph.b200_kind == 'euclidean' else 0
-            return kernels.score_exact(user_reprs, item_repr, user_bias, item_bias, mode=mode,
-                                       attention_repr=attention_reprs)
-        # user-defined prediction graph: its own dense form per taste, then the reference's collapse + bias order
-        with torch.no_grad():
-            preds = [pred_graph.connect_dense_prediction_graph(tf_user_representation=user_reprs[t],
-                                                               tf_item_representation=item_repr)
-                     for t in range(self.n_tastes)]
-            atts = None
-            if attention_reprs is not None:
-                atts = [pred_graph.connect_dense_prediction_graph(tf_user_representation=attention_reprs[t],
-                                                                  tf_item_representation=item_repr)
-                        for t in range(self.n_tastes)]
-            pred = collapse_mixture_of_tastes(preds, atts)
-            if self.biased:
-                pred = bias_prediction_dense(pred, user_bias, item_bias)
-        return pred.to(torch.float32).contiguous()
+    def _user_blocks(self, user_in, n_items, user_batch_size):
+        n_users = user_in.shape[0]
+        if user_batch_size is None:
+            user_batch_size = max(128, (self.PREDICT_BLOCK_BYTES // max(4 * n_items, 1)) // 128 * 128)
+        step = max(1, int(user_batch_size))
+        if step >= n_users:
+            return [(0, n_users, user_in)]
+        csr = user_in.matrix if isinstance(user_in.matrix, sp.csr_matrix) else sp.csr_matrix(user_in.matrix)
+        return [(u0, min(n_users, u0 + step), SparseInput(csr[u0:min(n_users, u0 + step)]))
+                for u0 in range(0, n_users, step)]
 
-    def predict(self, user_features, item_features):
-        """Scores for every user x item pair: float32 ndarray [n_users, n_items] (tensorrec/tensorrec.py:636-664)."""
+    def predict_batches(self, user_features, item_features, user_batch_size=None):
+        """predict() as a stream of user blocks: yields (u0, u1, scores float32 ndarray [u1 - u0, n_items]).
+
+        For results that fit neither HBM nor host memory at once (BASELINE config #2: 1M x 100K = 400 GB).  The item side
+        is computed once; user blocks are scored into two alternating device buffers and copied into two alternating
+        page-locked host buffers on a copy stream, so the device->host transfer of block b overlaps the kernels of block
+        b + 1 (the path is bound by the host link, not by HBM).  The yielded array IS the page-locked buffer: it stays
+        valid until the generator is advanced twice."""
         if self.tf_prediction is None:
             raise ModelNotFitException(method='predict')
         device = self._cuda_device()
         user_in = self._single_input(user_features, 'user_features')
         item_in = self._single_input(item_features, 'item_features')
-        return kernels.to_host(self._predict_device(user_in, item_in, device))
+        self._check_features(user_in, self.n_user_features, 'user')
+        self._check_features(item_in, self.n_item_features, 'item')
+        n_users, n_items = user_in.shape[0], item_in.shape[0]
+        if n_users == 0 or n_items == 0:
+            yield 0, n_users, np.zeros((n_users, n_items), dtype=np.float32)
+            return
+        blocks = self._user_blocks(user_in, n_items, user_batch_size)
+        rows = max(u1 - u0 for u0, u1, _ in blocks)
+        score = self._score_plan(item_in, device)
+        n_buf = min(2, len(blocks))
+        # the staging buffers (page-locking gigabytes takes seconds) are kept for the next call of the same shape
+        key = (rows, n_items, n_buf, str(device))
+        cached = getattr(self, '_stream_buffers', None)
+        if cached is None or cached[0] != key:
+            self._stream_buffers = None
+            cached = (key,
+                      [torch.empty((rows, n_items), dtype=torch.float32, device=device) for _ in range(n_buf)],
+                      [torch.empty((rows, n_items), dtype=torch.float32, pin_memory=True) for _ in range(n_buf)])
+            self._stream_buffers = cached
+        dev_buf, host_buf = cached[1], cached[2]
+        compute = torch.cuda.current_stream()
+        copier = torch.cuda.Stream(device=device)
+        copied = [None] * n_buf       # event: the copy out of dev_buf[j] / into host_buf[j] has finished
+        pending = None
+        for b, (u0, u1, block_in) in enumerate(blocks):
+            j = b % n_buf
+            if copied[j] is not None:
+                compute.wait_event(copied[j])          # the kernels of this block overwrite dev_buf[j]
+            score(block_in, out=dev_buf[j][:u1 - u0])
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copier):
+                copier.wait_event(done)
+                host_buf[j][:u1 - u0].copy_(dev_buf[j][:u1 - u0], non_blocking=True)
+                copied[j] = torch.cuda.Event()
+                copied[j].record(copier)
+            if pending is not None:                    # hand out block b - 1 while block b is being computed / copied
+                pj, p0, p1 = pending
+                copied[pj].synchronize()
+                yield p0, p1, host_buf[pj][:p1 - p0].numpy()
+            pending = (j, u0, u1)
+        pj, p0, p1 = pending
+        copied[pj].synchronize()
+        yield p0, p1, host_buf[pj][:p1 - p0].numpy()
+
+    def predict(self, user_features, item_features, out=None, user_batch_size=None):
+        """Scores for every user x item pair: float32 ndarray [n_users, n_items] (tensorrec/tensorrec.py:636-664).
+
+        Results larger than PREDICT_BLOCK_BYTES (or any result when user_batch_size / out is given) are produced in user
+        blocks (predict_batches) and assembled in `out` -- a caller-provided float32 array [n_users, n_items], e.g. a
+        numpy.memmap when the matrix exceeds host memory -- or in a new array."""
+        if self.tf_prediction is None:
+            raise ModelNotFitException(method='predict')
+        device = self._cuda_device()
+        user_in = self._single_input(user_features, 'user_features')
+        item_in = self._single_input(item_features, 'item_features')
+        n_users, n_items = user_in.shape[0], item_in.shape[0]
+        streamed = (out is not None or user_batch_size is not None or
+                    4 * n_users * n_items > self.PREDICT_BLOCK_BYTES)
+        if not streamed:
+            return kernels.to_host(self._predict_device(user_in, item_in, device))
+        if out is None:
+            out = np.empty((n_users, n_items), dtype=np.float32)
+        elif tuple(out.shape) != (n_users, n_items) or out.dtype != np.float32:
+            raise ValueError('out must be a float32 array of shape ({}, {})'.format(n_users, n_items))
+        for u0, u1, block in self.predict_batches(user_in, item_in, user_batch_size=user_batch_size):
+            out[u0:u1] = block
+        return out
 
     def predict_rank(self, user_features, item_features, k=None):
         """Ranks for every user x item pair: int32 ndarray [n_users, n_items], 1 = best, ties by lower item index
@@ -788,6 +923,7 @@ class TensorRec(object):
         state['_optimizer'] = None
         state['_optimizer_params'] = None
         state['_was_fit'] = self.tf_prediction is not None
+        state.pop('_stream_buffers', None)
         for name in self._all_hook_names():
             state[name] = None
         return state

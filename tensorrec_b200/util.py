@@ -18,8 +18,18 @@ def sample_items(n_items, n_users, n_sampled_items, replace, rng=None):
     else:
         if n_sampled_items > n_items:
             raise ValueError("Cannot take a larger sample than population when 'replace=False'")
-        # argpartition of iid uniforms: a uniformly random n_sampled_items-subset (in random order) per user
-        items = np.argsort(rng.random((n_users, n_items)), axis=1)[:, :n_sampled_items]
+        # a uniformly random n_sampled_items-subset per user = the positions of the n_sampled_items smallest of n_items
+        # iid uniforms (argpartition), in user chunks so that the temporary stays ~64 MB whatever n_users x n_items is
+        items = np.empty((n_users, n_sampled_items), dtype=np.int64)
+        chunk = max(1, (1 << 24) // max(n_items, 1))
+        for u0 in range(0, n_users, chunk):
+            u1 = min(n_users, u0 + chunk)
+            draws = rng.random((u1 - u0, n_items), dtype=np.float32)
+            if n_sampled_items < n_items:
+                part = np.argpartition(draws, n_sampled_items - 1, axis=1)[:, :n_sampled_items]
+            else:
+                part = np.argsort(draws, axis=1)
+            items[u0:u1] = part
     users = np.repeat(np.arange(n_users, dtype=np.int64), n_sampled_items)
     return np.stack([users, items.reshape(-1).astype(np.int64)], axis=1)
 

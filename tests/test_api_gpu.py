@@ -404,3 +404,41 @@ def test_wide_representations_are_tiled_over_k1(T):
     om = oracle.OracleModel([wu], wi)
     assert np.array_equal(model.predict_user_representation(uf), om.user_representation(uf)[0])
     assert np.array_equal(model.predict(uf, itf), om.predict(uf, itf))
+
+
+@pytest.mark.parametrize('kind', ['tensor', 'tastes', 'euclidean'])
+def test_streamed_predict_equals_one_shot(T, kind, tmp_path):
+    """predict() in user blocks (the form BASELINE config #2 needs: the 400 GB result never exists at once) is bit-identical
+    to the one-shot call, into a new array, a caller-provided array and a numpy.memmap; predict_batches covers every row
+    exactly once, in order."""
+    U, I, d = 700, 900, 64
+    uf, itf = H.tag_features(U, 200, 20, seed=1), H.tag_features(I, 200, 20, seed=2)
+    weights = {'linear_weights_item': H.linear_weights(200, d, seed=4),
+               'feature_biases_user': H.feature_biases(200, seed=5)[:, None],
+               'feature_biases_item': H.feature_biases(200, seed=6)[:, None]}
+    if kind == 'tastes':
+        model = T.TensorRec(n_components=d, n_tastes=3)
+        for t in range(3):
+            weights['linear_weights_user_%d' % t] = H.linear_weights(200, d, seed=10 + t)
+    else:
+        pg = T.prediction_graphs.EuclideanSimilarityPredictionGraph() if kind == 'euclidean' else \
+            T.prediction_graphs.DotProductPredictionGraph()
+        model = T.TensorRec(n_components=d, prediction_graph=pg)
+        weights['linear_weights_user_0'] = H.linear_weights(200, d, seed=3)
+    model.set_weights(weights)
+    whole = model.predict(uf, itf)
+    assert whole.shape == (U, I)
+    blocks = model.predict(uf, itf, user_batch_size=128)
+    assert np.array_equal(whole, blocks)
+    out = np.full((U, I), np.nan, dtype=np.float32)
+    assert model.predict(uf, itf, out=out, user_batch_size=300) is out and np.array_equal(out, whole)
+    mm = np.lib.format.open_memmap(str(tmp_path / 'scores.npy'), mode='w+', dtype=np.float32, shape=(U, I))
+    model.predict(uf, itf, out=mm, user_batch_size=256)
+    assert np.array_equal(np.asarray(mm), whole)
+    seen = []
+    for u0, u1, block in model.predict_batches(uf, itf, user_batch_size=200):
+        assert np.array_equal(block, whole[u0:u1])
+        seen.append((u0, u1))
+    assert seen == [(0, 200), (200, 400), (400, 600), (600, 700)]
+    with pytest.raises(ValueError):
+        model.predict(uf, itf, out=np.zeros((U, I + 1), np.float32))
