@@ -517,7 +517,8 @@ def run_extras(args):
     import copy
     extras = {}
     for name, fn, over in (('dense', run_dense, {'users': 65536, 'items': 100000, 'd': 64}),
-                           ('ranks', run_full_ranks, {'users': 8192, 'items': 131072, 'd': 128})):
+                           ('ranks', run_full_ranks, {'users': 8192, 'items': 131072, 'd': 128}),
+                           ('train', run_train, {'users': 1000000, 'items': 1000000, 'd': 128})):
         a = copy.copy(args)
         for key, val in over.items():
             setattr(a, key, val)
@@ -720,6 +721,123 @@ def run_full_ranks(args, emit=True):
     return result
 
 
+def run_train(args, emit=True):
+    """Secondary measurement (BASELINE configs[3]: WMRBLossGraph sampled-rank training step, d=128, bf16): one Adam step of
+    LinearRepr x DotProduct x WMRB over `--users` users x `--items` items on the kernels of tensorrec_b200/train_kernels.py --
+    K1 forward, device sampler, fused serial-prediction + WMRB forward / backward, K1^T backward, fused L2 + Adam.
+    metric: (user, item) pairs scored AND back-propagated per second = users x (n_sampled + interactions per user) / step.
+    Bound: HBM (one item-row gather per pair + the sparse products + the optimiser's pass over every weight)."""
+    import torch
+    import tensorrec_b200
+    from tensorrec_b200 import kernels, train_kernels
+    from tensorrec_b200.input_utils import SparseInput
+    kernels.require_cuda()
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    uf, itf, wu, wi, bu, bi = make_problem(args)
+    n_users, n_items, d, n_s = args.users, args.items, args.d, args.n_sampled
+    rng = np.random.default_rng(5)
+    per_user = 4                                            # positive interactions per user, + 1 negative in 4 users
+    rows = np.repeat(np.arange(n_users, dtype=np.int64), per_user)
+    cols = rng.integers(0, n_items, rows.shape[0])
+    vals = np.ones(rows.shape[0], dtype=np.float32)
+    neg_rows = np.arange(0, n_users, 4, dtype=np.int64)
+    interactions = sp.csr_matrix((np.concatenate([vals, -np.ones(neg_rows.shape[0], np.float32)]),
+                                  (np.concatenate([rows, neg_rows]),
+                                   np.concatenate([cols, rng.integers(0, n_items, neg_rows.shape[0])]))),
+                                 shape=(n_users, n_items))
+    bf16 = args.train_dtype == 'bf16'
+
+    def new_model(users=None):
+        model = tensorrec_b200.TensorRec(n_components=d, loss_graph=tensorrec_b200.loss_graphs.WMRBLossGraph())
+        model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
+                           'feature_biases_item': bi[:, None]})
+        return model, train_kernels.WmrbStep(model, dev, seed=0, bf16=bf16)
+
+    model, stepper = new_model()
+    int_in, uf_in, if_in = SparseInput(interactions), SparseInput(uf), SparseInput(itf)
+    n_pos = int_in.n_positive
+    lr, l2 = 0.01, n_pos * 1e-5
+
+    def step():
+        return stepper.step(int_in, uf_in, if_in, n_s, lr, l2)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    stepper.marks = []
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        loss, _ = step()
+    s1.record()
+    torch.cuda.synchronize()
+    ms = s0.elapsed_time(s1) / args.steps
+    names = ['representations', 'sampler', 'wmrb_step', 'weight_gradients', 'adam']
+    phase = {n: 0.0 for n in names}
+    marks = stepper.marks
+    per = len(names) + 1
+    for s in range(args.steps):
+        for j, n in enumerate(names):
+            phase[n] += marks[s * per + j][1].elapsed_time(marks[s * per + j + 1][1]) / args.steps
+    stepper.marks = None
+    loss_sum = float(loss.sum())
+    pairs = float(n_users) * n_s + interactions.nnz
+    esz = 2 if bf16 else 4
+    n_w = (uf.shape[1] + itf.shape[1]) * (d + 1)
+    k1 = lambda m, r: m.nnz * 8 + (r + 1) * 4 + m.shape[1] * d * 4 + r * d * 4        # noqa: E731  (SURVEY 8d per side)
+    alg_bytes = (k1(uf, n_users) + k1(itf, n_items)                        # representations
+                 + ((n_users + n_items) * d * (4 + 2) if bf16 else 0)      # rounding pass
+                 + n_users * n_s * 4                                       # sampler
+                 + pairs * d * esz + n_users * d * (esz + 4) + n_users * n_s * 4 + interactions.nnz * 24
+                 + 2 * n_items * d * 4                                     # wmrb: item rows, user rows, dU, zero + write dI
+                 + (uf.nnz + itf.nnz) * (8 + d * 4) + n_w * 4              # K1^T: gathered gradient rows, weight gradients
+                 + n_w * 4 * 7)                                            # Adam: read w, g, m, v; write w, m, v
+    peaks = measured_peaks()
+
+    # CPU oracle beside it: the same step (forward + backward) on a bounded user sample, item side complete
+    from oracle import loss_ops
+    n_cpu = min(n_users, args.train_cpu_users)
+    sub_int, sub_uf = interactions[:n_cpu], uf[:n_cpu]
+    m2, st2 = new_model()
+    st2.t = stepper.t - 1                                   # same sampler step as the last timed step
+    samples = train_kernels.sample_items_device(n_items, n_cpu, n_s, False, 0, st2.t, dev)
+    loss2, _ = st2.step(SparseInput(sub_int), SparseInput(sub_uf), if_in, n_s, lr, l2, samples=samples)
+    t0 = time.perf_counter()
+    ref = loss_ops.wmrb_step_reference(sub_uf, itf, sub_int, wu, wi, bu, bi, samples.cpu().numpy(),
+                                       round_repr=loss_ops.round_to_bfloat16 if bf16 else None)
+    cpu_s = time.perf_counter() - t0
+    cpu_pairs = float(n_cpu) * n_s + sub_int.nnz
+    g_gpu = st2.last['grads']['linear_weights_item'].cpu().numpy()
+    scale = max(1.0, float(np.abs(ref['d_w_item']).max()))
+    parity = {'users_checked': int(n_cpu),
+              'loss_sum_rel_err': abs(float(loss2.sum()) - float(ref['loss'].sum())) / max(1e-30, abs(float(ref['loss'].sum()))),
+              'item_weight_grad_max_abs_err_over_scale': float(np.abs(g_gpu - ref['d_w_item']).max() / scale),
+              'against': 'oracle/loss_ops.wmrb_step_reference (numpy forward + analytic backward, same samples)'}
+    result = {'metric': 'wmrb_train_pairs_per_s', 'value': pairs / (ms * 1e-3), 'unit': 'pairs/s', 'n_gpus': 1,
+              'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'dtype': args.train_dtype + ' representations, '
+              'f32 weights / accumulation / Adam',
+              'config': {'workload': 'WMRB sampled-rank training step, %d users x %d items, d=%d, n_sampled_items=%d, '
+                                     '%d interactions (BASELINE configs[3] shape: the slice of 10M x 1M run per step)'
+                                     % (n_users, n_items, d, n_s, interactions.nnz),
+                         'loss_sum_last_step': loss_sum},
+              'phases_ms': {k: round(v, 4) for k, v in phase.items()},
+              'roofline': {'kernel': 'whole step (K1 x2, sampler, wmrb_step_kernel, K1^T x2, adam_step_kernel x4)',
+                           'bound': 'hbm', 'achieved': alg_bytes / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                           'unit': 'GB/s', 'frac': alg_bytes / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                           'algorithmic_bytes': int(alg_bytes),
+                           'wmrb_kernel_gather_gbs': pairs * d * esz / (phase['wmrb_step'] * 1e-3) / 1e9},
+              'cpu_baseline': {'value': cpu_pairs / cpu_s, 'unit': 'pairs/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                               'sample': '%d of %d users (all items): numpy forward + backward of the same step, %.1f s'
+                                         % (n_cpu, n_users, cpu_s)},
+              'parity': parity}
+    del model, stepper, m2, st2
+    torch.cuda.empty_cache()
+    if emit:
+        print(json.dumps(result), flush=True)
+    return result
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -730,7 +848,7 @@ def main():
     ap.add_argument('--items', type=int, default=1000000)
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--k', type=int, default=10)
-    ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks'])
+    ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks', 'train'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--parity-users', type=int, default=4096, help='users checked against the oracle at full size')
@@ -741,11 +859,16 @@ def main():
                     help='development aid (1 GPU): time the work of ONE item shard out of this many, no exchange')
     ap.add_argument('--no-clocks', action='store_true', help='do not sample nvidia-smi during the timed region')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads of the default run')
+    ap.add_argument('--n-sampled', type=int, default=64, help='--workload train: n_sampled_items')
+    ap.add_argument('--train-dtype', default='bf16', choices=['bf16', 'f32'], help='--workload train: representations')
+    ap.add_argument('--train-cpu-users', type=int, default=20000, help='--workload train: users of the CPU oracle sample')
     args = ap.parse_args()
     if args.workload == 'dense':
         run_dense(args)
     elif args.workload == 'ranks':
         run_full_ranks(args)
+    elif args.workload == 'train':
+        run_train(args)
     elif args.impl == 'reference':
         run_reference(args)
     else:

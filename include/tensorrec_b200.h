@@ -244,6 +244,45 @@ int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_
                    int32_t k_in, int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score,
                    int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * The sampled-rank training step: everything of one Adam step of
+ * LinearRepresentationGraph x DotProductPredictionGraph x WMRBLossGraph / BalancedWMRBLossGraph that is not a
+ * sparse x dense product (those are trk_csr_gather_reduce_f32 on the CSR of the features and of their transpose).
+ *
+ * trk_sample_items   replaces sample_items behind tf.py_func (tensorrec/util.py:12-21, tensorrec/tensorrec.py:298-302):
+ *                    out[u, j] (int32 [n_users, n_sampled]) = item ids drawn for user u, with replacement (uniform) or
+ *                    without (Floyd's algorithm: a uniformly random n_sampled-subset; n_sampled <= 4096), from the
+ *                    counter-based Philox4x32-10 stream (seed, step, user, draw).  trk_sample_stream_u64 exposes that
+ *                    stream on the host (tests reproduce a device sample from it).
+ * trk_wmrb_step      forward and backward between the representations and the loss, one warp per user:
+ *                      pred(u, i) = (sum_k user_repr[u, k] * item_repr[i, k] + user_bias[u]) + item_bias[i]
+ *                                   (tensorrec/prediction_graphs.py:52-55, recommendation_graphs.py:44-57)
+ *                      for every stored interaction n = (u, i, val) (CSR by user, reference COO order) with val > 0:
+ *                        loss[n] = log(n_items / n_sampled * sum_j max(0, 1 - pred(u, i) + pred(u, samples[u, j]))
+ *                                      [* val / item_weight_sum[i]]  + 1)     (tensorrec/loss_graphs.py:153-180, 190-227)
+ *                      loss[n] = 0 for val <= 0; pred_serial[n] = pred(u, i) for every n;
+ *                      gradients of sum_n loss[n]: d_user_repr [n_users, d] and d_user_bias [n_users] are written,
+ *                      d_item_repr [n_items, d] and d_item_bias [n_items] are ADDED to with red.global.add (zero them
+ *                      first; the order of the floating-point additions is not fixed, as in tf.gather's GPU gradient).
+ *                    Representations are fp32 or bf16 (repr_is_bf16; BASELINE config #4 allows bf16), arithmetic and
+ *                    gradients fp32.  coef [nnz] is scratch.  Constraints: d % 4 == 0, d <= 512, n_sampled <= 2048.
+ * trk_f32_to_bf16    round-to-nearest-even conversion of a representation for the bf16 form.
+ * trk_adam_step_f32  tf.train.AdamOptimizer on (grad + l2 * w) (tensorrec/tensorrec.py:487-489):
+ *                      m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  w -= lr_t m / (sqrt(v) + epsilon),
+ *                    lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) formed by the caller.
+ * ---------------------------------------------------------------------------------------------------- */
+int trk_sample_items(int64_t n_users, int64_t n_items, int32_t n_sampled, int32_t replace, uint64_t seed,
+                     uint32_t step, int32_t* out, void* stream);
+uint64_t trk_sample_stream_u64(uint64_t seed, uint32_t step, uint32_t user, uint32_t draw);
+int trk_wmrb_step(const void* user_repr, const void* item_repr, int32_t repr_is_bf16, const float* user_bias,
+                  const float* item_bias, const int32_t* inter_indptr, const int32_t* inter_item,
+                  const float* inter_val, const float* item_weight_sum, const int32_t* samples, int64_t n_users,
+                  int64_t n_items, int32_t d, int32_t n_sampled, float* loss, float* pred_serial, float* coef,
+                  float* d_user_repr, float* d_user_bias, float* d_item_repr, float* d_item_bias, void* stream);
+int trk_f32_to_bf16(const float* x, int64_t n, void* out, void* stream);
+int trk_adam_step_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                      float epsilon, float l2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

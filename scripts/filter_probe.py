@@ -54,10 +54,6 @@ pairs = A.users * float(A.items)
 print('shape %d users x %d items, d=%d' % (A.users, A.items, A.d))
 ms = timeit(run_filter)
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
-for st in ('0', '4', '8', '16', '32'):
-    os.environ['TRK_FILTER_SCAN_TILES'] = st
-    print('filter kernel, scan prologue of %s tiles: %.2f ms' % (st, timeit(run_filter)))
-os.environ.pop('TRK_FILTER_SCAN_TILES')
 os.environ['TRK_FILTER_NO_WARMSTART'] = '1'
 print('filter kernel, no threshold prologue at all: %.2f ms' % timeit(run_filter))
 os.environ.pop('TRK_FILTER_NO_WARMSTART')

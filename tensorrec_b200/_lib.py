@@ -56,6 +56,13 @@ SIGNATURES = {
     'trk_gather_operand_rows': (ctypes.c_int, [_c_p, _c_p, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_i32, _c_p, _c_p, _c_p,
                                                _c_p]),
     'trk_scatter_topk_rows': (ctypes.c_int, [_c_p, _c_p, _c_i32, _c_p, _c_p, _c_i64, _c_i32, _c_p, _c_p, _c_i64, _c_p]),
+    'trk_sample_items': (ctypes.c_int, [_c_i64, _c_i64, _c_i32, _c_i32, ctypes.c_uint64, ctypes.c_uint32, _c_p, _c_p]),
+    'trk_sample_stream_u64': (ctypes.c_uint64, [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    'trk_wmrb_step': (ctypes.c_int, [_c_p, _c_p, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32,
+                                     _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    'trk_f32_to_bf16': (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p]),
+    'trk_adam_step_f32': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_i64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_float, _c_p]),
 }
 
 _lib = None

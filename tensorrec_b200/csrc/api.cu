@@ -62,6 +62,14 @@ int gather_operand_rows(const int32_t*, int32_t*, int32_t, int32_t, const void*,
 int scatter_topk_rows(const int32_t*, const int32_t*, int32_t, const float*, const int32_t*, int64_t, int32_t, float*,
                       int32_t*, int64_t, cudaStream_t);
 
+int sample_items(int64_t, int64_t, int32_t, int32_t, uint64_t, uint32_t, int32_t*, cudaStream_t);
+int wmrb_step(const void*, const void*, int32_t, const float*, const float*, const int32_t*, const int32_t*, const float*,
+              const float*, const int32_t*, int64_t, int64_t, int32_t, int32_t, float*, float*, float*, float*, float*,
+              float*, float*, cudaStream_t);
+int f32_to_bf16(const float*, int64_t, void*, cudaStream_t);
+int adam_step(float*, const float*, float*, float*, int64_t, float, float, float, float, float, cudaStream_t);
+uint64_t philox_u64_host(uint64_t, uint32_t, uint32_t, uint32_t);
+
 static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 }  // namespace trk
@@ -207,6 +215,34 @@ int trk_scatter_topk_rows(const int32_t* idx, const int32_t* counters, int32_t c
                           int32_t* out_item, int64_t out_row_stride, void* stream) {
   return trk::scatter_topk_rows(idx, counters, capacity, sub_score, sub_item, sub_row_stride, k, out_score, out_item,
                                 out_row_stride, trk::as_stream(stream));
+}
+
+int trk_sample_items(int64_t n_users, int64_t n_items, int32_t n_sampled, int32_t replace, uint64_t seed,
+                     uint32_t step, int32_t* out, void* stream) {
+  return trk::sample_items(n_users, n_items, n_sampled, replace, seed, step, out, trk::as_stream(stream));
+}
+
+uint64_t trk_sample_stream_u64(uint64_t seed, uint32_t step, uint32_t user, uint32_t draw) {
+  return trk::philox_u64_host(seed, step, user, draw);
+}
+
+int trk_wmrb_step(const void* user_repr, const void* item_repr, int32_t repr_is_bf16, const float* user_bias,
+                  const float* item_bias, const int32_t* inter_indptr, const int32_t* inter_item,
+                  const float* inter_val, const float* item_weight_sum, const int32_t* samples, int64_t n_users,
+                  int64_t n_items, int32_t d, int32_t n_sampled, float* loss, float* pred_serial, float* coef,
+                  float* d_user_repr, float* d_user_bias, float* d_item_repr, float* d_item_bias, void* stream) {
+  return trk::wmrb_step(user_repr, item_repr, repr_is_bf16, user_bias, item_bias, inter_indptr, inter_item, inter_val,
+                        item_weight_sum, samples, n_users, n_items, d, n_sampled, loss, pred_serial, coef, d_user_repr,
+                        d_user_bias, d_item_repr, d_item_bias, trk::as_stream(stream));
+}
+
+int trk_f32_to_bf16(const float* x, int64_t n, void* out, void* stream) {
+  return trk::f32_to_bf16(x, n, out, trk::as_stream(stream));
+}
+
+int trk_adam_step_f32(float* w, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                      float epsilon, float l2, void* stream) {
+  return trk::adam_step(w, grad, m, v, n, lr_t, beta1, beta2, epsilon, l2, trk::as_stream(stream));
 }
 
 }  // extern "C"

@@ -75,7 +75,6 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
-  int32_t scan_tiles;          // tiles at the start of a long sweep that are first only SCANNED for a threshold (0 = off)
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
   float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
@@ -247,11 +246,44 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t 
   }
 }
 
+// Bit mask of the columns of acc[0, 16) whose admission bound passes: 16 independent compares and an OR tree (a serial
+// `mask |= ...` chain put ~80 cycles of dependent latency into every slow-path entry).
+__device__ __forceinline__ uint32_t pass_mask_16(const uint32_t* acc, float bmax_scaled, float tau) {
+  uint32_t b[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) b[j] = (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
+#pragma unroll
+  for (int s = 8; s > 0; s >>= 1) {
+#pragma unroll
+    for (int j = 0; j < s; ++j) b[j] |= b[j + s];
+  }
+  return b[0];
+}
+// Appends the columns of `mask` (a 16-column half, its maximum `amax` known from the hot loop).  One passing column -- the
+// normal case -- IS the maximum of its half (x -> x + bmax is monotonic, so the largest accumulator passes whenever any
+// does): one store, no search through the registers.  Several: every slot is addressed by a prefix popcount, the
+// stores are independent.
+__device__ __forceinline__ void append_16(const uint32_t* acc, uint32_t mask, float amax, int32_t pos_base,
+                                          uint32_t buf_row_addr, int& cnt) {
+  if ((mask & (mask - 1u)) == 0u) {
+    f_sts64(buf_row_addr + cnt * 8, amax, pos_base + __ffs(mask) - 1);
+    cnt += 1;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if ((mask >> j) & 1u)
+        f_sts64(buf_row_addr + (cnt + __popc(mask & ((1u << j) - 1u))) * 8, __uint_as_float(acc[j]), pos_base + j);
+    }
+    cnt += __popc(mask);
+  }
+}
+
 // 32 columns behind ONE vote (the two 16-column maxima are independent chains).  Slow path, taken when some lane's bound
-// passes: the hitting lanes form the pass mask of all 32 columns, ONE ballot tells whether every row's buffer can take
-// its new entries -- the common case: the hitting lanes append, nobody else does anything -- and only otherwise the
-// chunk goes through the two-step path (compact the rows that need it, append 16 columns at a time so that the 32-entry
-// buffer cannot overflow between compactions).
+// passes (~8 % of the chunks of a 1M-item sweep, ~40 % at a 125K-item shard: 32 rows share the instruction stream): the
+// hitting lanes form the pass masks, ONE ballot tells whether every row's buffer can take its new entries -- the common
+// case: the hitting lanes append, nobody else does anything -- and only otherwise the chunk goes through the two-step
+// path (compact the rows that need it, append 16 columns at a time so that the 32-entry buffer cannot overflow between
+// compactions).
 __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base, float bmax_scaled, const AdmitCtx& ctx,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
                                           float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
@@ -259,25 +291,12 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
   const float a0 = acc_max_16(acc), a1 = acc_max_16(acc + 16);
   const bool h0 = a0 + bmax_scaled > tau, h1 = a1 + bmax_scaled > tau;
   if (__any_sync(0xffffffffu, h0 || h1)) {
-    uint32_t pass = 0;
-    if (h0) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pass |= (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
-    }
-    if (h1) {
-#pragma unroll
-      for (int j = 16; j < 32; ++j) pass |= (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
-    }
-    if (__ballot_sync(0xffffffffu, cnt + __popc(pass) > kBufEntries) == 0u) {
-      if (pass != 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if ((pass >> j) & 1u) {
-            f_sts64(buf_row_addr + cnt * 8, __uint_as_float(acc[j]), pos_base + j);
-            cnt += 1;
-          }
-        }
-      }
+    uint32_t lo = 0, hi = 0;
+    if (h0) lo = pass_mask_16(acc, bmax_scaled, tau);
+    if (h1) hi = pass_mask_16(acc + 16, bmax_scaled, tau);
+    if (__ballot_sync(0xffffffffu, cnt + __popc(lo) + __popc(hi) > kBufEntries) == 0u) {
+      if (lo != 0u) append_16(acc, lo, a0, pos_base, buf_row_addr, cnt);
+      if (hi != 0u) append_16(acc + 16, hi, a1, pos_base + 16, buf_row_addr, cnt);
     } else {
       admit_16(acc, h0, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, n_res,
                lane, k);
@@ -294,7 +313,11 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
 // its row of the first accumulator to 16 group maxima (8 columns each), sorts them in registers and takes the k-th
 // largest, A: k DIFFERENT columns have acc >= A, their biases are >= the block minimum, so the k-th best approximate
 // score of the tile is >= fma(A, c, ub) + bmin and theta may start 2.25 m below that.  The tile is then filtered as
-// usual: ~1.5 k admissions per row instead of 128, no compaction.
+// usual: ~1.5 k admissions per row instead of 128, no compaction.  (Measured at the 125K-item shard: -1.3 ms of 35.
+// Scanning MORE tiles first -- 4 to 32 tiles reduced to a running top-16 of group maxima, then filtered in a second
+// pass -- gained nothing: profiles/probe_r2_filter_shard8_scan_prologue.txt.  The cost of the admission path is
+// proportional to the number of 32-column chunks in which ANY of a warp's 32 rows passes its bound, ~25 ns of SM time
+// each at either size, and the early tiles are few chunks whatever they admit.)
 __device__ __forceinline__ float acc_max_8(const uint32_t* acc) {
   return fmaxf(fmaxf(fmaxf(__uint_as_float(acc[0]), __uint_as_float(acc[1])),
                      fmaxf(__uint_as_float(acc[2]), __uint_as_float(acc[3]))),
@@ -316,37 +339,6 @@ __device__ __forceinline__ void sort16_desc(float (&g)[16]) {
           g[i] = desc ? hi : lo;
           g[j] = desc ? lo : hi;
         }
-      }
-    }
-  }
-}
-
-// ---- scan prologue of a long sweep ----------------------------------------------------------------------------------
-// A streaming top-k admits k (1 + ln(n / k)) items, and HALF of those admissions fall into the first sqrt(n) items: with
-// the 32 rows of a warp sharing one instruction stream the epilogue took its slow path in ~40 % of the 32-column chunks
-// of a 125K-item shard (8-GPU run: 6.5 ms of 30 per rank went into admissions; TRK_FILTER_DEBUG=4 vs 0).  So the first
-// `scan_tiles` tiles of a sweep are processed TWICE.  Pass 0 admits nothing: every thread keeps the 16 largest GROUP
-// maxima (8 columns per group) of its row in registers (per tile: the 16 group maxima are sorted and merged into the
-// running list by a bitonic merge) -- at the end k different columns are known to reach the k-th largest group maximum,
-// which (with the smallest bias of the scanned tiles) bounds the k-th best approximate score from below.  Pass 1 then
-// filters the same tiles with that threshold already in place: ~1.5 k admissions instead of k (1 + ln(128 scan_tiles / k)),
-// no compaction.  Cost: scan_tiles extra tiles of tensor work per sweep (8 of 977 at the shard size, 16 of 7813 at 1M).
-__device__ __forceinline__ int unit_scan_tiles(int t0, int t1, int scan_tiles, bool enabled) {
-  return (enabled && scan_tiles > 0 && t1 - t0 >= 4 * scan_tiles) ? scan_tiles : 0;
-}
-// r (sorted descending) <- the 16 largest of r and g (g sorted descending): elementwise max against the reversed g
-// leaves a bitonic sequence that holds them, four half-cleaner stages sort it
-__device__ __forceinline__ void merge16_desc(float (&r)[16], const float (&g)[16]) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = fmaxf(r[i], g[15 - i]);
-#pragma unroll
-  for (int stride = 8; stride > 0; stride >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if ((i & stride) == 0) {
-        const float hi = fmaxf(r[i], r[i + stride]), lo = fminf(r[i], r[i + stride]);
-        r[i] = hi;
-        r[i + stride] = lo;
       }
     }
   }
@@ -418,9 +410,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         const int sp = static_cast<int>(w / n_groups);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        const int ns = unit_scan_tiles(t0, t1, p.scan_tiles, p.block_bias_min != nullptr && p.debug_mode == 0);
-        for (int i = 0; i < ns + (t1 - t0); ++i) {     // the first ns tiles twice: scan pass, then the sweep
-          const int t = i < ns ? t0 + i : t0 + (i - ns);
+        for (int t = t0; t < t1; ++t) {
           if (p.debug_mode == 6 && filled >= static_cast<uint32_t>(n_slots)) continue;   // timing: no B stream
           mbar_wait(b_empty + ts, ts_phase ^ 1);
           if (elect_one()) {
@@ -470,12 +460,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0) continue;
-        const int ns = unit_scan_tiles(t0, t1, p.scan_tiles, p.block_bias_min != nullptr && p.debug_mode == 0);
         mbar_wait(a_full + 0, witer & 1);   // both groups have written their user block into tensor memory
         mbar_wait(a_full + 1, witer & 1);
         tcgen05_fence_after();
         ++witer;
-        for (int i = 0; i < ns + (t1 - t0); ++i) {
+        for (int t = t0; t < t1; ++t) {
           const bool streamed = !(p.debug_mode == 6 && consumed >= static_cast<uint32_t>(n_slots));
           if (streamed) mbar_wait(b_full + ts, ts_phase);
           const uint64_t db = umma_desc_k_major_sw128(b_base + ts * kSlotBytes);
@@ -571,62 +560,15 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         if (lane == 0) mbar_arrive(a_full + group);
       }
 
-      const int ns = unit_scan_tiles(t0, t1, p.scan_tiles, p.block_bias_min != nullptr && p.debug_mode == 0);
-      const int n_iter = ns + (t1 - t0);
       float bmax_next = t1 > t0 ? __ldg(p.block_bias_max + t0) : 0.0f;
-      float scan_top[16];   // scan pass: the 16 largest group maxima of this row so far (descending)
-#pragma unroll
-      for (int q = 0; q < 16; ++q) scan_top[q] = kNegInf;
-      for (int i = 0; i < n_iter; ++i) {
-        const int t = i < ns ? t0 + i : t0 + (i - ns);
+      for (int t = t0; t < t1; ++t) {
         const float bmax_scaled = bmax_next * inv_c;
-        if (i + 1 < n_iter) {   // in flight while this tile is filtered
-          const int t_next = i + 1 < ns ? t0 + i + 1 : t0 + (i + 1 - ns);
-          bmax_next = __ldg(p.block_bias_max + t_next);
-        }
+        if (t + 1 < t1) bmax_next = __ldg(p.block_bias_max + t + 1);   // in flight while this tile is filtered
         mbar_wait(tmem_full + slot, slot_use & 1);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
-        if (i < ns) {
-          // ---- scan pass: nothing is admitted; the tile's 16 group maxima are merged into scan_top ----
-          float g[16];
-          tmem_ld_32x32b_x32(taddr, ra);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 32, rb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[q] = acc_max_8(ra + 8 * q);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 64, ra);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[4 + q] = acc_max_8(rb + 8 * q);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 96, rb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[8 + q] = acc_max_8(ra + 8 * q);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[12 + q] = acc_max_8(rb + 8 * q);
-          sort16_desc(g);
-          merge16_desc(scan_top, g);
-          if (i == ns - 1) {
-            // k different columns of the scanned tiles reach scan_top[k - 1]; their biases are >= the smallest block
-            // minimum of those tiles (the last one when the items are in descending-bias order)
-            float bmin = __ldg(p.block_bias_min + t0);
-            for (int q = 1; q < ns; ++q) bmin = fminf(bmin, __ldg(p.block_bias_min + t0 + q));
-            float a_k = scan_top[0];
-#pragma unroll
-            for (int q = 1; q < 16; ++q) a_k = (q < p.k) ? scan_top[q] : a_k;
-            const float th0 = (fmaf(a_k, c, ubias) + bmin) - m3;
-            if (th0 == th0 && bmin > kNegInf) {
-              theta = th0;
-              const float tt = (theta - ubias) * inv_c;
-              tau = tt - 8.0f * 1.1920929e-7f * fabsf(tt) - 1e-30f;
-            }
-          }
-          goto drained;
-        }
-        if (t == t0 && ns == 0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
+        if (t == t0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
           const float bmin = __ldg(p.block_bias_min + t0);   // the same for the whole CTA: warp-uniform branch
           if (bmin > kNegInf) {
             float g[16];
@@ -917,12 +859,6 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
   p.n_user_pairs = static_cast<int32_t>(ceil_div(n_users, 2 * kFBlockM));
   p.item_id_offset = item_id_offset;
-  {
-    // scan prologue: 8 tiles (1K items) for sweeps of 32+ tiles, 16 for 512+ tiles; TRK_FILTER_SCAN_TILES overrides (0 = off)
-    const char* env = getenv("TRK_FILTER_SCAN_TILES");
-    p.scan_tiles = env != nullptr ? atoi(env) : (p.tiles_per_split >= 512 ? 16 : 8);
-    if (p.scan_tiles < 0 || p.scan_tiles > 64) p.scan_tiles = 0;
-  }
   p.cand_score = cand_score;
   p.cand_item = cand_item;
   p.row_theta = row_theta;

@@ -110,6 +110,21 @@ class SparseInput(object):
             self._csr[key] = DeviceCSR.from_scipy_transposed(self.matrix, device=device)
         return self._csr[key]
 
+    @property
+    def n_positive(self):
+        """Stored interactions with a value > 0 (the entries WMRB's positive_interaction_mask keeps)."""
+        if getattr(self, '_n_positive', None) is None:
+            self._n_positive = int(np.count_nonzero(np.asarray(self.matrix.data) > 0))
+        return self._n_positive
+
+    def positive_item_sums(self, device):
+        """BalancedWMRBLossGraph's per-item sum of the positive interaction values, on the device."""
+        key = 'possum:' + str(device)
+        if key not in self._csr:
+            from .train_kernels import positive_item_sums
+            self._csr[key] = torch.from_numpy(positive_item_sums(self.matrix, self.shape[1])).to(device)
+        return self._csr[key]
+
     def torch_sparse(self, device):
         """Uncoalesced COO tensor in reference entry order (duplicates are summed by torch.sparse.mm)."""
         key = str(device)

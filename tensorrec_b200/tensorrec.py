@@ -388,11 +388,29 @@ class TensorRec(object):
                 self._optimizer = None
 
     def _fit_epochs(self, batches, epochs, learning_rate, alpha, batched_alpha, verbose, n_sampled_items, device):
+        from . import train_kernels
+        on_kernels = device.type == 'cuda' and train_kernels.eligible(self) and \
+            (n_sampled_items is None or n_sampled_items <= 2048)
         for epoch in range(epochs):
             for batch, (int_in, uf_in, if_in) in enumerate(batches):
                 if uf_in.shape[1] != self.n_user_features or if_in.shape[1] != self.n_item_features:
                     raise ValueError('feature matrices have {} / {} columns but the model was built for {} / {}'.format(
                         uf_in.shape[1], if_in.shape[1], self.n_user_features, self.n_item_features))
+                if on_kernels:
+                    # the sampled-rank step on hand-written kernels (train_kernels.py)
+                    if getattr(self, '_wmrb_step', None) is None or self._wmrb_step.device != device:
+                        self._wmrb_step = train_kernels.WmrbStep(self, device)
+                    n_pos = int_in.n_positive
+                    loss_vec, serial_predictions = self._wmrb_step.step(
+                        int_in, uf_in, if_in, n_sampled_items, learning_rate, l2=n_pos * batched_alpha)
+                    self._stepped = True
+                    if verbose:
+                        mean_loss = float(loss_vec.sum()) / max(n_pos, 1)
+                        mean_pred = float(torch.mean(serial_predictions))
+                        wr = sum(0.5 * float(torch.sum(w.detach() * w.detach())) for w in self._variables.values())
+                        logging.info('EPOCH {} BATCH {} loss = {}, weight_reg_l2_loss = {}, mean_pred = {}'.format(
+                            epoch, batch, mean_loss, alpha * wr, mean_pred))
+                    continue
                 with variable_scope(self._variables):
                     basic_loss, wr_loss, serial_predictions, tf_weights = self._training_losses(
                         int_in, uf_in, if_in, n_sampled_items, device)
@@ -435,6 +453,7 @@ class TensorRec(object):
             t = torch.as_tensor(np.asarray(value, dtype=np.float32)).to(device).clone()
             self._variables[name] = t.requires_grad_(True)
         self._optimizer = None
+        self._wmrb_step = None          # Adam moments of the kernel training path belong to the replaced weights
         if n_user_features is None and 'linear_weights_user_0' in self._variables:
             n_user_features = self._variables['linear_weights_user_0'].shape[0]
         if n_item_features is None and 'linear_weights_item' in self._variables:
@@ -924,6 +943,7 @@ class TensorRec(object):
         state['_optimizer_params'] = None
         state['_was_fit'] = self.tf_prediction is not None
         state.pop('_stream_buffers', None)
+        state['_wmrb_step'] = None
         for name in self._all_hook_names():
             state[name] = None
         return state
