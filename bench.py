@@ -62,22 +62,51 @@ def make_weights(n_features, d, seed):
     return w
 
 
+def movielens_shaped(users, items, seed):
+    """SURVEY C3 (examples/getting_started.py:57-58, 164): identity user features; item features = identity + 18 binary
+    genre columns, 1-3 genres per item."""
+    rng = np.random.default_rng(seed)
+    uf = sp.identity(users, dtype=np.float32, format='csr')
+    n_genres = rng.integers(1, 4, items)
+    r = np.repeat(np.arange(items, dtype=np.int64), n_genres)
+    c = items + rng.integers(0, 18, r.shape[0])
+    itf = sp.csr_matrix((np.ones(items + r.shape[0], dtype=np.float32),
+                         (np.concatenate([np.arange(items, dtype=np.int64), r]),
+                          np.concatenate([np.arange(items, dtype=np.int64), c]))), shape=(items, items + 18))
+    itf.sum_duplicates()
+    itf.data[:] = 1.0
+    return uf, itf
+
+
 def make_problem(args):
+    """--scores iid: the headline inputs (normal weights: continuous scores, ties have probability zero);
+    ties: integer-valued weights and biases on the same features (massive exact ties: the reference's normal case before
+    training -- indicator features, integer ratings); c3: MovieLens-shaped features, cosine prediction."""
     t0 = time.time()
-    uf = indicator_csr(args.users, seed=0)
-    itf = indicator_csr(args.items, seed=1)
-    wu = make_weights(uf.shape[1], args.d, seed=2)
-    wi = make_weights(itf.shape[1], args.d, seed=3)
+    scores = getattr(args, 'scores', 'iid')
+    if scores == 'c3':
+        uf, itf = movielens_shaped(args.users, args.items, seed=0)
+    else:
+        uf = indicator_csr(args.users, seed=0)
+        itf = indicator_csr(args.items, seed=1)
     rng = np.random.default_rng(4)
-    bu = (0.1 * rng.standard_normal(uf.shape[1])).astype(np.float32)
-    bi = (0.1 * rng.standard_normal(itf.shape[1])).astype(np.float32)
+    if scores == 'ties':
+        wu = rng.integers(-2, 3, size=(uf.shape[1], args.d)).astype(np.float32)
+        wi = rng.integers(-2, 3, size=(itf.shape[1], args.d)).astype(np.float32)
+        bu = rng.integers(-3, 4, size=uf.shape[1]).astype(np.float32)
+        bi = rng.integers(-3, 4, size=itf.shape[1]).astype(np.float32)
+    else:
+        wu = make_weights(uf.shape[1], args.d, seed=2)
+        wi = make_weights(itf.shape[1], args.d, seed=3)
+        bu = (0.1 * rng.standard_normal(uf.shape[1])).astype(np.float32)
+        bi = (0.1 * rng.standard_normal(itf.shape[1])).astype(np.float32)
     log('[bench] synthetic problem built in %.1fs: users %s nnz %d, items %s nnz %d, d=%d'
         % (time.time() - t0, uf.shape, uf.nnz, itf.shape, itf.nnz, args.d))
     return uf, itf, wu, wi, bu, bi
 
 
 # ----------------------------------------------------------------------------------------------------- CPU oracle leg
-def cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, budget_s, threads):
+def cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, budget_s, threads, cosine=False):
     """Times the oracle (reference semantics: SpMM, fp32 GEMM, bias adds, the literal double full sort per user,
     then the rank <= k entries) on a bounded sample of users against ALL items.  Returns (pairs_per_s, description).
 
@@ -87,6 +116,8 @@ def cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, budget_s, threads):
     n_users, n_items = uf.shape[0], itf.shape[0]
     t0 = time.perf_counter()
     item_repr = R.sparse_dense_matmul_fast(itf, wi)
+    if cosine:
+        item_repr = R.l2_normalize(item_repr)
     item_bias = np.asarray(itf @ bi, dtype=np.float32)
     t_items = time.perf_counter() - t0
 
@@ -101,6 +132,8 @@ def cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, budget_s, threads):
     def run(u0, u1):
         sub = uf[u0:u1]
         user_repr = R.sparse_dense_matmul_fast(sub, wu)
+        if cosine:
+            user_repr = R.l2_normalize(user_repr)
         user_bias = np.asarray(sub @ bu, dtype=np.float32)
         scores = R.bias_prediction_dense(R.dot_product_dense(user_repr, item_repr), user_bias, item_bias)
         rows_per = max(1, (u1 - u0 + threads - 1) // threads)
@@ -205,24 +238,34 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def workload_string(args):
     """config.workload: the same string in both arms (the driver compares them)."""
+    scores = getattr(args, 'scores', 'iid')
+    if scores == 'c3':
+        return ('predict_rank top-%d, %d users x %d items, d=%d, MovieLens-shaped features (identity users; identity + 18 '
+                'genre columns items), LinearRepr x CosineSimilarity, biased (BASELINE configs[2] structure, SURVEY C3, '
+                'scaled up)' % (args.k, args.users, args.items, args.d))
     return ('predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, LinearRepr x DotProduct, biased '
-            '(BASELINE configs[4] shape at the size the metric is quoted on; SURVEY C5)'
-            % (args.k, args.users, args.items, args.d))
+            '(BASELINE configs[4] shape at the size the metric is quoted on; SURVEY C5)%s'
+            % (args.k, args.users, args.items, args.d,
+               '' if scores == 'iid' else '; INTEGER-valued weights and biases: massive exact ties'))
 
 
 PHASES = ['k1_users', 'items_prep', 'filter', 'rescore', 'fallback', 'exchange', 'merge']
 
 
-def oracle_topk_rows(uf, itf, wu, wi, bu, bi, rows, k, item_repr=None, item_bias=None):
+def oracle_topk_rows(uf, itf, wu, wi, bu, bi, rows, k, item_repr=None, item_bias=None, cosine=False):
     """Reference-semantics top-k (oracle) of the given user rows against ALL items (CPU)."""
     from oracle import reference_ops as R
     if item_repr is None:
         item_repr = R.sparse_dense_matmul_fast(itf, wi)
+        if cosine:
+            item_repr = R.l2_normalize(item_repr)
         item_bias = np.asarray(itf @ bi, dtype=np.float32)
     out = np.empty((len(rows), k), dtype=np.int32)
     for c0 in range(0, len(rows), 512):
         sub = uf[rows[c0:c0 + 512]]
         user_repr = R.sparse_dense_matmul_fast(sub, wu)
+        if cosine:
+            user_repr = R.l2_normalize(user_repr)
         user_bias = np.asarray(sub @ bu, dtype=np.float32)
         scores = R.bias_prediction_dense(R.dot_product_dense(user_repr, item_repr), user_bias, item_bias)
         out[c0:c0 + 512] = R.top_k_from_scores_fast(scores, k)[0]
@@ -272,6 +315,8 @@ def run_b200(args):
 
     use_filter = args.topk_path == 'filter' and k <= kernels.filter_max_k()
     last = {}
+    cosine = args.scores == 'c3'
+    n_norm = 1 if cosine else 0          # CosineSimilarityPredictionGraph: both representations L2-normalised in K1
 
     def step(record=False):
         marks = []
@@ -283,14 +328,16 @@ def run_b200(args):
                 marks.append(e)
 
         mark()
-        out = kernels.gather_reduce(ucsr, wu_d, want_f32=False, split_d_pad=d_pad, want_norm=use_filter)
+        out = kernels.gather_reduce(ucsr, wu_d, n_normalize=n_norm, want_f32=False, split_d_pad=d_pad,
+                                    want_norm=use_filter)
         us, usc = out[1], out[2]
         user_norm = out[3] if use_filter else None
         ub = kernels.project_biases(ucsr, bu_d)
         users = kernels.SideOperands(None, us, usc, ub, n_users, d, d_pad, norm=user_norm)
         mark()
         stats = torch.empty((3,), dtype=torch.float32, device=dev) if use_filter else None
-        _, its, isc = kernels.gather_reduce(icsr, wi_d, want_f32=False, split_d_pad=d_pad, stats=stats)
+        _, its, isc = kernels.gather_reduce(icsr, wi_d, n_normalize=n_norm, want_f32=False, split_d_pad=d_pad,
+                                            stats=stats)
         ib = kernels.project_biases(icsr, bi_d)
         items = kernels.SideOperands(None, its, isc, ib, n_local, d, d_pad, stats=stats)
         if use_filter:
@@ -305,6 +352,11 @@ def run_b200(args):
             # rows whose bound could not be certified go through the exact kernel, routed on the device
             counters, cap = kernels.rerun_uncertified(users, items, bad, top, k, item_id_offset=lo)
             last['counters'], last['cap'], last['bad'] = counters, cap, bad
+            if args.scores != 'iid' and int(counters[0]) > cap:
+                # more rejected rows than the device-side fallback holds (tie-heavy scores): what the API does at its
+                # final synchronisation -- the whole batch through the exact kernel (this check synchronises)
+                top = kernels.topk_exact(users, items, k, item_id_offset=lo)
+                last['overflow'] = True
         else:
             meta = kernels.pack_item_meta(isc, ib, n_local)
             mark()
@@ -381,9 +433,12 @@ def run_b200(args):
         return sp.csr_matrix((arrs[0].numpy(), arrs[1].numpy(), arrs[2].numpy()), shape=m.shape), arrs
 
     del ucsr, icsr, out
+    last_overflow = last.get('overflow', False)
     last.clear()
     tensorrec_b200.tensorrec.TOPK_PATH = 'auto' if use_filter else 'exact'
-    model = tensorrec_b200.TensorRec(n_components=d)
+    model = tensorrec_b200.TensorRec(
+        n_components=d, prediction_graph=(tensorrec_b200.prediction_graphs.CosineSimilarityPredictionGraph() if cosine
+                                          else tensorrec_b200.prediction_graphs.DotProductPredictionGraph()))
     model.set_weights({'linear_weights_user_0': wu, 'linear_weights_item': wi, 'feature_biases_user': bu[:, None],
                        'feature_biases_item': bi[:, None]})
     uf_host, _keep_u = pinned_csr(uf)
@@ -434,14 +489,15 @@ def run_b200(args):
     k1_gbs = k1_survey_bytes / (k1u_ms * 1e-3) / 1e9
 
     cores = os.cpu_count() or 1
-    cpu_value, cpu_desc, cpu_s, cpu_top = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, args.cpu_budget, cores)
+    cpu_value, cpu_desc, cpu_s, cpu_top = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, args.cpu_budget, cores,
+                                                         cosine=cosine)
     # parity at the full item count: the reference-semantics ranking (oracle, CPU) of the first users of this rank's
     # slice AND of the rows the certificate rejected in the last step, against the GPU top-k of the same users; only
     # sub-tolerance near-ties may order differently (fp32 rounding of the two GEMMs)
     t0 = time.perf_counter()
     rows = np.concatenate([np.arange(u_lo, u_lo + n_check), fallback_ids]).astype(np.int64)
     emulating = world == 1 and n_shards > 1
-    exp, _, _ = oracle_topk_rows(uf, itf_local if emulating else itf, wu, wi, bu, bi, rows, k)
+    exp, _, _ = oracle_topk_rows(uf, itf_local if emulating else itf, wu, wi, bu, bi, rows, k, cosine=cosine)
     exp = exp + (lo if emulating else 0)
     got = np.concatenate([top_items_check, fallback_items]) if len(fallback_ids) else top_items_check
     agree = float((exp == got).mean()) if len(rows) else None
@@ -467,7 +523,8 @@ def run_b200(args):
                    'parallelism': ('item-sharded x%d: 1 NCCL all-to-all of the per-shard top-k, each rank merges its '
                                    'user slice' % world) if world > 1 else 'single GPU',
                    'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
-                   'fallback_rows_last_step': fallback_rows,
+                   'fallback_rows_last_step': fallback_rows, 'scores': args.scores,
+                   'fallback_overflow_whole_batch_exact': bool(last_overflow),
                    'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
                    % ((n_users + n_local) * 2 * d_pad * 2 / 1e6, (wu.nbytes + wi.nbytes) / 1e6)},
         'clocks': clocks,
@@ -538,11 +595,12 @@ def run_reference(args):
     uf, itf, wu, wi, bu, bi = make_problem(args)
     cores = os.cpu_count() or 1
     per_step_budget = max(2.0, min(args.cpu_budget, 90.0 / max(1, args.steps + args.warmup)))
+    cosine = args.scores == 'c3'
     for _ in range(args.warmup):
-        cpu_oracle_leg(uf, itf, wu, wi, bu, bi, args.k, per_step_budget, cores)
+        cpu_oracle_leg(uf, itf, wu, wi, bu, bi, args.k, per_step_budget, cores, cosine=cosine)
     values, secs, desc = [], 0.0, ''
     for _ in range(args.steps):
-        v, desc, s, _ = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, args.k, per_step_budget, cores)
+        v, desc, s, _ = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, args.k, per_step_budget, cores, cosine=cosine)
         values.append(v)
         secs += s
     value = float(np.mean(values))
@@ -850,6 +908,9 @@ def main():
     ap.add_argument('--k', type=int, default=10)
     ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks', 'train'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
+    ap.add_argument('--scores', default='iid', choices=['iid', 'ties', 'c3'],
+                    help='score distribution of the top-k workload: continuous (headline), integer-valued (massive ties), '
+                         'or MovieLens-shaped features with cosine prediction')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--parity-users', type=int, default=4096, help='users checked against the oracle at full size')
     ap.add_argument('--parity-fallback-rows', type=int, default=1024,

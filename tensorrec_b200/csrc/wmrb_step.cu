@@ -73,14 +73,21 @@ sample_items_kernel(int64_t n_users, uint32_t n_items, int n_sampled, uint64_t s
       for (int j = lane; j < n_sampled; j += 32)
         row[j] = static_cast<int32_t>(bounded(philox_u64(seed, step, static_cast<uint32_t>(u), j), n_items));
     } else {
-      for (int jj = 0; jj < n_sampled; ++jj) {
+      // the S Philox blocks are independent: lanes draw them in parallel (t_jj uniform in [0, n_items - S + jj]) ...
+      for (int jj = lane; jj < n_sampled; jj += 32) {
         const uint32_t j = n_items - static_cast<uint32_t>(n_sampled) + jj;
-        const int32_t t = static_cast<int32_t>(bounded(philox_u64(seed, step, static_cast<uint32_t>(u), jj), j + 1));
+        chosen[jj] = static_cast<int32_t>(bounded(philox_u64(seed, step, static_cast<uint32_t>(u), jj), j + 1));
+      }
+      __syncwarp();
+      // ... only the "already taken?" test is sequential: entry jj is compared with the final entries [0, jj)
+      for (int jj = 1; jj < n_sampled; ++jj) {
+        const int32_t t = chosen[jj];
         bool found = false;
         for (int q = lane; q < jj; q += 32) found |= chosen[q] == t;
-        found = __any_sync(0xffffffffu, found);
-        if (lane == 0) chosen[jj] = found ? static_cast<int32_t>(j) : t;
-        __syncwarp();
+        if (__any_sync(0xffffffffu, found)) {
+          if (lane == 0) chosen[jj] = static_cast<int32_t>(n_items - static_cast<uint32_t>(n_sampled) + jj);
+          __syncwarp();
+        }
       }
       for (int j = lane; j < n_sampled; j += 32) row[j] = chosen[j];
       __syncwarp();
