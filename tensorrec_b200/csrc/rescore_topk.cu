@@ -44,6 +44,46 @@ __device__ __forceinline__ void load_split4(const __half* __restrict__ row, int 
   }
 }
 
+// Sum over the 32 lanes of 16 values per lane, all 16 at once: at every halving step a lane keeps half of its values and
+// hands the other half to its partner (8 + 4 + 2 + 1 shuffles), a last exchange completes the sum: 16 shuffles instead of
+// 16 x 5.  Afterwards lanes 2c and 2c + 1 both hold the total of value c.  Fixed order: deterministic.
+__device__ __forceinline__ float transpose_sum_16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// bitonic sort of one (score, id) entry per lane into (score desc, id asc) order; sentinels (-inf, INT32_MAX) go last
+__device__ __forceinline__ void warp_sort_desc(float& s, int32_t& id, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, s, stride);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, id, stride);
+      const bool lower = (lane & stride) == 0;
+      const bool descending = (lane & size) == 0;
+      const bool other_first = r_before(os, oi, s, id);
+      const bool take_other = (lower == descending) ? other_first : !other_first;
+      if (take_other) {
+        s = os;
+        id = oi;
+      }
+    }
+  }
+}
+
+// One warp per user, 16 candidates (one filter list) at a time: the 16 item rows are requested together, the 16 dot
+// products are reduced by one transposed reduction, the survivors are ordered by one 32-lane bitonic sort (even lanes:
+// the new candidates, odd lanes: the best 16 of the lists before).
 __global__ void __launch_bounds__(256)
 rescore_topk_kernel(const __half* __restrict__ user_split, const float* __restrict__ user_scale,
                     const __half* __restrict__ item_split, const float* __restrict__ item_scale,
@@ -68,48 +108,50 @@ rescore_topk_kernel(const __half* __restrict__ user_split, const float* __restri
     const float su = __ldg(user_scale + u);
     const float ub = user_bias != nullptr ? __ldg(user_bias + u) : 0.0f;
     const int32_t* ci = cand_item + u * n_cand;
-    // running top-k: lane j holds the j-th best so far
-    float ls = kNegInf;
-    int32_t li = 0x7fffffff;
+    float best_s = kNegInf;        // after a group: lanes 0..15 hold the best 16 so far, in order
+    int32_t best_i = 0x7fffffff;
     int n_real = 0;
 
-    for (int c0 = 0; c0 < n_cand; c0 += 4) {
-      int32_t ids[4];
-      float iv[4][4];
-      float isc[4], ibs[4];
+    for (int c0 = 0; c0 < n_cand; c0 += 16) {
+      // lane l < 16 owns candidate c0 + l (id, validity, row index); every lane needs every id for the row loads
+      int32_t my_id = (lane < 16 && c0 + lane < n_cand) ? __ldg(ci + c0 + lane) : 0x7fffffff;
+      const int64_t my_local = static_cast<int64_t>(my_id) - item_id_offset;
+      const bool my_ok = my_id != 0x7fffffff && my_local >= 0 && my_local < n_items_local;
+      if (!my_ok) my_id = 0x7fffffff;
+      n_real += __popc(__ballot_sync(0xffffffffu, my_ok));
+      float part[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        ids[q] = (c0 + q < n_cand) ? __ldg(ci + c0 + q) : 0x7fffffff;
-        const int64_t local = static_cast<int64_t>(ids[q]) - item_id_offset;
-        const bool ok = ids[q] != 0x7fffffff && local >= 0 && local < n_items_local;
-        if (!ok) ids[q] = 0x7fffffff;
-        load_split4(item_split + (ok ? local : 0) * row_halves, d_pad, lane, ok, iv[q]);
-        isc[q] = ok ? __ldg(item_scale + local) : 0.0f;
-        ibs[q] = (ok && item_bias != nullptr) ? __ldg(item_bias + local) : 0.0f;
+      for (int q = 0; q < 16; ++q) {
+        const int32_t id = __shfl_sync(0xffffffffu, my_id, q);
+        const bool ok = id != 0x7fffffff;                      // warp-uniform
+        float iv[4];
+        load_split4(item_split + (ok ? static_cast<int64_t>(id) - item_id_offset : 0) * row_halves, d_pad, lane, ok, iv);
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fmaf(uv[j], iv[j], acc);
+        part[q] = acc;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (ids[q] == 0x7fffffff) continue;   // warp-uniform: ids are broadcast loads
-        float part = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) part = fmaf(uv[j], iv[q][j], part);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        const float s = fmaf(part, isc[q] * su, ub) + ibs[q];   // the bias arithmetic of the exact kernel's epilogue
-        // insert (s, id) into the lane-distributed sorted list
-        const unsigned before = __ballot_sync(0xffffffffu, r_before(ls, li, s, ids[q]));
-        const int pos = __popc(before);
-        const float up_s = __shfl_up_sync(0xffffffffu, ls, 1);
-        const int32_t up_i = __shfl_up_sync(0xffffffffu, li, 1);
-        if (lane == pos) {
-          ls = s;
-          li = ids[q];
-        } else if (lane > pos) {
-          ls = up_s;
-          li = up_i;
-        }
-        n_real += 1;
+      const float dot = transpose_sum_16(part, lane);           // lanes 2c, 2c + 1: candidate c0 + c
+      const int owner = lane >> 1;
+      int32_t id = __shfl_sync(0xffffffffu, my_id, owner);
+      float s = kNegInf;
+      if ((lane & 1) == 0 && id != 0x7fffffff) {
+        const int64_t local = static_cast<int64_t>(id) - item_id_offset;
+        const float ib = item_bias != nullptr ? __ldg(item_bias + local) : 0.0f;
+        s = fmaf(dot, __ldg(item_scale + local) * su, ub) + ib;   // the bias arithmetic of the exact kernel's epilogue
+      } else {
+        id = 0x7fffffff;
       }
+      // odd lanes: the best 16 of the groups before (lane 2j + 1 takes entry j)
+      const float prev_s = __shfl_sync(0xffffffffu, best_s, owner);
+      const int32_t prev_i = __shfl_sync(0xffffffffu, best_i, owner);
+      if ((lane & 1) != 0) {
+        s = prev_s;
+        id = prev_i;
+      }
+      warp_sort_desc(s, id, lane);
+      best_s = s;
+      best_i = id;
     }
 
     // verification of the filter's bound for this user
@@ -117,13 +159,13 @@ rescore_topk_kernel(const __half* __restrict__ user_split, const float* __restri
     for (int l = lane; l < n_lists; l += 32) theta_max = fmaxf(theta_max, __ldg(row_theta + u * n_lists + l));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) theta_max = fmaxf(theta_max, __shfl_xor_sync(0xffffffffu, theta_max, o));
-    const float kth = __shfl_sync(0xffffffffu, ls, k - 1);
+    const float kth = __shfl_sync(0xffffffffu, best_s, k - 1);
     const float m = kRMarginFactor * __ldg(user_norm + u) * max_item_norm + kRBiasUlps * (fabsf(ub) + max_item_bias);
     bool valid = m < -kNegInf;   // an infinite (or NaN) margin certifies nothing
     if (theta_max > kNegInf) valid = valid && (n_real >= k) && (theta_max + m < kth);
     if (lane < k) {
-      out_score[u * out_stride + lane] = ls;
-      out_item[u * out_stride + lane] = li;
+      out_score[u * out_stride + lane] = best_s;
+      out_item[u * out_stride + lane] = best_i;
     }
     if (lane == 0) out_flag[u] = valid ? 0 : 1;
   }
@@ -254,7 +296,8 @@ int rescore_topk(const void* user_split, const float* user_scale, const void* it
   TRK_CHECK_ARG(out_score && out_item && out_flag, "rescore_topk: null output");
   TRK_CHECK_ARG(n_users >= 0 && n_items_local >= 0 && n_lists >= 1 && list_width >= 1, "rescore_topk: bad sizes");
   TRK_CHECK_ARG(d_pad == 64 || d_pad == 128, "rescore_topk: d_pad=%d (64 or 128)", d_pad);
-  TRK_CHECK_ARG(k >= 1 && k <= 32, "rescore_topk: k=%d outside [1, 32]", k);
+  TRK_CHECK_ARG(k >= 1 && k <= 16, "rescore_topk: k=%d outside [1, 16]", k);
+  TRK_CHECK_ARG(list_width <= 16 || list_width % 16 == 0, "rescore_topk: list_width=%d", list_width);
   TRK_CHECK_ARG(out_row_stride >= k, "rescore_topk: out_row_stride=%lld < k", static_cast<long long>(out_row_stride));
   TRK_CHECK_ARG(reinterpret_cast<uintptr_t>(user_split) % 16 == 0 && reinterpret_cast<uintptr_t>(item_split) % 16 == 0,
                 "rescore_topk: operands must be 16-byte aligned");

@@ -131,26 +131,62 @@ struct AdmitCtx {
 // Entries [n_res, cnt) of the buffer are RAW -- (accumulator value, processing position) exactly as the hot loop
 // found them; they are turned into (approximate score, item id) here, where the bias and permutation lookups of all
 // of them are independent loads issued by different lanes (one L2 latency per compaction, not one per admission).
-__device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int src, int k, int& cnt, int& n_res,
-                                            float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
-                                            float inv_c, const AdmitCtx& ctx) {
+//
+// Split in two so that the lookups of the NEXT row to compact are in flight while THIS row is sorted: the rows of a warp
+// overflow in bursts (their thresholds rise in step), a compaction is ~250 instructions, an L2 round trip ~700 cycles.
+struct RowFetch {
+  float s;        // raw accumulator (lanes >= n_res) or resolved approximate score
+  int32_t id;     // processing position (raw) or item id (resolved)
+  float bias;     // bias of the raw entry's position           } requested by compact_fetch,
+  int32_t perm;   // original item index of that position       } first used by compact_finish
+  int n, n_res;
+  uint32_t addr;
+};
+__device__ __forceinline__ float ldg_nc_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int32_t ldg_nc_s32(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ RowFetch compact_fetch(uint32_t buf_row_addr, int lane, int src, int cnt, int n_res,
+                                                  const AdmitCtx& ctx) {
+  RowFetch f;
+  f.n = __shfl_sync(0xffffffffu, cnt, src);
+  f.n_res = __shfl_sync(0xffffffffu, n_res, src);
+  f.addr = __shfl_sync(0xffffffffu, buf_row_addr, src);
+  f.s = -__int_as_float(0x7f800000);
+  f.id = 0x7fffffff;
+  f.bias = 0.0f;
+  f.perm = 0;
+  if (lane < f.n) {
+    f_lds64(f.addr + lane * 8, &f.s, &f.id);
+    if (lane >= f.n_res) {
+      f.bias = ldg_nc_f32(ctx.bias + f.id);
+      // (a padded column of the last tile can be appended -- its bias is -inf, it never survives -- and has no perm entry)
+      f.perm = (ctx.perm != nullptr && f.id < ctx.n_items) ? ldg_nc_s32(ctx.perm + f.id) : f.id;
+    }
+  }
+  return f;
+}
+__device__ __forceinline__ void compact_finish(const RowFetch& f, int lane, int src, int k, int& cnt, int& n_res,
+                                               float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
+                                               float inv_c, const AdmitCtx& ctx) {
   const float kNegInf = -__int_as_float(0x7f800000);
-  const int n = __shfl_sync(0xffffffffu, cnt, src);
-  const int nr = __shfl_sync(0xffffffffu, n_res, src);
-  const uint32_t addr = __shfl_sync(0xffffffffu, buf_row_addr, src);
+  const int n = f.n;
+  const uint32_t addr = f.addr;
   const float m3s = __shfl_sync(0xffffffffu, m3, src);
   const float cs = __shfl_sync(0xffffffffu, c, src);
   const float ubs = __shfl_sync(0xffffffffu, ubias, src);
-  float s = kNegInf;
-  int32_t id = 0x7fffffff;
-  if (lane < n) {
-    f_lds64(addr + lane * 8, &s, &id);
-    if (lane >= nr) {
-      const int32_t pos = id;
-      const float b = __ldg(ctx.bias + pos);
-      id = pos < ctx.n_items ? ctx.id_offset + (ctx.perm != nullptr ? __ldg(ctx.perm + pos) : pos) : 0x7fffffff;
-      s = fmaf(s, cs, ubs) + b;   // approximate score: (acc * c + user bias) + item bias
-    }
+  float s = f.s;
+  int32_t id = f.id;
+  if (lane < n && lane >= f.n_res) {
+    const int32_t pos = id;
+    id = pos < ctx.n_items ? ctx.id_offset + f.perm : 0x7fffffff;
+    s = fmaf(s, cs, ubs) + f.bias;   // approximate score: (acc * c + user bias) + item bias
   }
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
@@ -196,6 +232,25 @@ __device__ __forceinline__ void compact_row(uint32_t buf_row_addr, int lane, int
   }
   __syncwarp();
 }
+// compacts every row of `rows` (bit = lane), the lookups of the next row in flight while the current one is sorted
+__device__ __forceinline__ void compact_rows(unsigned rows, uint32_t buf_row_addr, int lane, int k, int& cnt, int& n_res,
+                                             float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
+                                             float inv_c, const AdmitCtx& ctx) {
+  if (rows == 0u) return;
+  int src = __ffs(rows) - 1;
+  rows &= rows - 1;
+  RowFetch cur = compact_fetch(buf_row_addr, lane, src, cnt, n_res, ctx);
+  while (true) {
+    const int nxt = rows != 0u ? __ffs(rows) - 1 : -1;
+    rows &= rows - 1;     // (0 stays 0)
+    RowFetch ahead = cur;
+    if (nxt >= 0) ahead = compact_fetch(buf_row_addr, lane, nxt, cnt, n_res, ctx);
+    compact_finish(cur, lane, src, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+    if (nxt < 0) break;
+    cur = ahead;
+    src = nxt;
+  }
+}
 
 // 16 columns of one user row per lane.  The admission test is v_j = acc_j + bias_j / c > tau.  Items are processed in
 // bias-sorted order, so the biases of one 128-item block differ by ~1e-4 of their range and v_j <= max_j acc_j +
@@ -229,12 +284,8 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t 
     for (int j = 0; j < 16; ++j) pass |= (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
   }
   __syncwarp();   // earlier appends of every lane are visible to the lanes that may now compact its row
-  unsigned need = __ballot_sync(0xffffffffu, cnt + __popc(pass) > kBufEntries);
-  while (need) {
-    const int src = __ffs(need) - 1;
-    need &= need - 1;
-    compact_row(buf_row_addr, lane, src, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
-  }
+  const unsigned need = __ballot_sync(0xffffffffu, cnt + __popc(pass) > kBufEntries);
+  compact_rows(need, buf_row_addr, lane, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
   if (pass != 0) {   // cnt + popc(pass) <= kBufEntries holds here (a compaction leaves at most kKeepMax = 16)
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -640,8 +691,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       }
 
       // end of the item range: final compaction of every row of this warp, then emit the survivors
-      for (int src = 0; src < 32; ++src)
-        compact_row(buf_row_addr, lane, src, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+      compact_rows(0xffffffffu, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
       if (u_ok) {
         const int64_t base = u * p.n_splits + sp;
         float* os = p.cand_score + base * kKeepMax;
