@@ -239,10 +239,15 @@ int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const
  * Entry j of list l of user u is read at cand_*[u * user_stride + l * list_stride + j]:
  *   one GPU, [n_users, n_lists, k_in]:                user_stride = n_lists * k_in, list_stride = k_in;
  *   exchange receive buffer [n_lists, n_users, 2k]:   user_stride = 2k, list_stride = n_users * 2k, cand_item = cand_score + k.
- * Row u of the result goes to out_*[u * out_row_stride ...].  n_users_live: see trk_score_topk_f16x3. */
+ * Row u of the result goes to out_*[u * out_row_stride ...].  n_users_live: see trk_score_topk_f16x3.
+ * dedup != 0: the lists of a user may name the same item -- the per-TASTE top-k lists of a mixture-of-tastes model,
+ * whose prediction is the maximum over the tastes (collapse_mixture_of_tastes, tensorrec/recommendation_graphs.py:107):
+ * every item is emitted once, with its best score (k_out <= 32).  The top-k of max_t s_t(u, .) is contained in the union
+ * of the per-taste top-k lists, so n_tastes fused top-k sweeps + this merge give the model's top-k without the
+ * [n_users, n_items] matrix. */
 int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
                    int32_t k_in, int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score,
-                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, void* stream);
+                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, int32_t dedup, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * The sampled-rank training step: everything of one Adam step of

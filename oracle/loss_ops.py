@@ -178,15 +178,26 @@ def wmrb_step_reference(user_features, item_features, interactions, w_user, w_it
     }
 
 
+def adam_learning_rate(learning_rate, t, beta1=0.9, beta2=0.999):
+    """lr sqrt(1 - beta2^t) / (1 - beta1^t) as TensorFlow forms it: float32 throughout, the powers are float32 variables
+    multiplied by float32(beta) once per step (training_ops.cc ApplyAdam; adam.py _finish)."""
+    b1p, b2p = F32(1.0), F32(1.0)
+    for _ in range(int(t)):
+        b1p, b2p = F32(b1p * F32(beta1)), F32(b2p * F32(beta2))
+    return F32(F32(learning_rate) * np.sqrt(F32(1.0) - b2p) / (F32(1.0) - b1p))
+
+
 def adam_reference(w, grad, m, v, t, learning_rate, l2=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8):
     """tf.train.AdamOptimizer (defaults as the reference uses it, tensorrec.py:489) on grad + l2 * w; t = 1, 2, ...
+    The arithmetic of TensorFlow's ApplyAdam functor, float32:
+        m += (g - m) (1 - beta1);  v += (g g - v) (1 - beta2);  w -= (m lr_t) / (sqrt(v) + epsilon).
     Returns (w, m, v) after the step."""
     w, grad, m, v = (np.asarray(a, dtype=F32) for a in (w, grad, m, v))
     g = grad + F32(l2) * w
-    m = F32(beta1) * m + F32(1.0 - beta1) * g
-    v = F32(beta2) * v + F32(1.0 - beta2) * g * g
-    lr_t = F32(learning_rate * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
-    return (w - lr_t * m / (np.sqrt(v) + F32(epsilon))).astype(F32), m.astype(F32), v.astype(F32)
+    m = m + (g - m) * (F32(1.0) - F32(beta1))
+    v = v + (g * g - v) * (F32(1.0) - F32(beta2))
+    lr_t = adam_learning_rate(learning_rate, t, beta1, beta2)
+    return (w - (m * lr_t) / (np.sqrt(v) + F32(epsilon))).astype(F32), m.astype(F32), v.astype(F32)
 
 
 def round_to_bfloat16(x):

@@ -44,7 +44,7 @@ int score_topk_f16x3(const void*, const float*, const float*, const void*, const
 int score_dense_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
                       float*, int64_t, cudaStream_t);
 int topk_merge(const float*, const int32_t*, int64_t, int32_t, int32_t, int32_t, int64_t, int64_t, float*, int32_t*,
-               int64_t, const int32_t*, cudaStream_t);
+               int64_t, const int32_t*, int32_t, cudaStream_t);
 int score_filter_max_k();
 int score_filter_list_width();
 int operand_stats(const void*, const float*, int64_t, int32_t, float*, float*, cudaStream_t);
@@ -151,9 +151,9 @@ int trk_score_dense_f16x3(const void* user_split, const float* user_scale, const
 
 int trk_topk_merge(const float* cand_score, const int32_t* cand_item, int64_t n_users, int32_t n_lists,
                    int32_t k_in, int32_t k_out, int64_t user_stride, int64_t list_stride, float* out_score,
-                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, void* stream) {
+                   int32_t* out_item, int64_t out_row_stride, const int32_t* n_users_live, int32_t dedup, void* stream) {
   return trk::topk_merge(cand_score, cand_item, n_users, n_lists, k_in, k_out, user_stride, list_stride, out_score,
-                         out_item, out_row_stride, n_users_live, trk::as_stream(stream));
+                         out_item, out_row_stride, n_users_live, dedup, trk::as_stream(stream));
 }
 
 int trk_score_filter_max_k(void) { return trk::score_filter_max_k(); }

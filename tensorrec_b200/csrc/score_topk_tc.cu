@@ -200,6 +200,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   constexpr int n_kb2 = 2 * kNKB;
+  // work item w = (user block w / n_splits, item split w % n_splits): the splits of ONE user block go to consecutive
+  // CTAs, so a handful of live user blocks (the device-side fallback: ~100 rows of a million) still spreads over the
+  // whole machine -- with the block index minor, one live block of 8 x 148 items landed on 37 of the 148 CTAs
   const int64_t n_work = static_cast<int64_t>(p.n_user_blocks) * p.n_splits;
   // user blocks at or beyond this one hold no rows (every role skips them: the same test in all three loops)
   const int live_blocks = p.n_users_live != nullptr
@@ -240,8 +243,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
       uint32_t witer = 0;  // non-empty work items so far
       uint32_t it = 0;     // tiles issued so far
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int ub = static_cast<int>(w % p.n_user_blocks);
-        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int ub = static_cast<int>(w / p.n_splits);
+        const int sp = static_cast<int>(w % p.n_splits);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
         if (t1 <= t0 || ub >= live_blocks) continue;
@@ -293,10 +296,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
       const uint32_t a_base = smem_u32(smem + L.a_off);
       const uint32_t b_base = smem_u32(smem + L.b_off);
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = static_cast<int>(w / p.n_user_blocks);
+        const int sp = static_cast<int>(w % p.n_splits);
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        if (t1 <= t0 || static_cast<int>(w % p.n_user_blocks) >= live_blocks) continue;
+        if (t1 <= t0 || static_cast<int>(w / p.n_splits) >= live_blocks) continue;
         mbar_wait(a_full, witer & 1);
         ++witer;
         for (int t = t0; t < t1; ++t, ++it) {
@@ -356,8 +359,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_users, const __grid_cons
     const uint32_t stage_base = smem_u32(smem + L.list_score_off) + static_cast<uint32_t>(warp - 4) * 2u * kStoreTileBytes;
 
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int ub = static_cast<int>(w % p.n_user_blocks);
-      const int sp = static_cast<int>(w / p.n_user_blocks);
+      const int ub = static_cast<int>(w / p.n_splits);
+      const int sp = static_cast<int>(w % p.n_splits);
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
       if (ub >= live_blocks) continue;

@@ -341,19 +341,21 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_
     out[i] = __float2bfloat16_rn(x[i]);
 }
 
-// Adam as tf.train.AdamOptimizer applies it (lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) is formed by the host):
-//   g = grad + l2 * w;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  w -= lr_t m / (sqrt(v) + eps)
+// Adam as TensorFlow's ApplyAdam kernel evaluates it, in float32 (lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) is formed by the
+// host, with the running float32 powers of the betas):
+//   g = grad + l2 * w;  m += (g - m) (1 - b1);  v += (g g - v) (1 - b2);  w -= (m lr_t) / (sqrt(v) + eps)
 __global__ void adam_step_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m,
                                  float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps, float l2) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float wi = w[i];
-    const float g = fmaf(l2, wi, grad[i]);
-    const float mi = fmaf(b1, m[i], (1.0f - b1) * g);
-    const float vi = fmaf(b2, v[i], (1.0f - b2) * g * g);
+    const float g = grad[i] + l2 * wi;
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.0f - b1);
+    vi = vi + (g * g - vi) * (1.0f - b2);
     m[i] = mi;
     v[i] = vi;
-    w[i] = wi - lr_t * mi / (sqrtf(vi) + eps);
+    w[i] = wi - (mi * lr_t) / (sqrtf(vi) + eps);
   }
 }
 

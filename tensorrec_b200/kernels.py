@@ -332,21 +332,23 @@ def topk_merge(cand_score, cand_item, k_out, out=None, n_users_live=None):
     if out is None:
         out = PackedTopK(n_users, k_out, cand_score.device)
     rc = lib.trk_topk_merge(_p(cand_score), _p(cand_item), n_users, n_lists, k_in, int(k_out), n_lists * k_in, k_in,
-                            out.score_ptr(), out.item_ptr(), 2 * out.k, _p(n_users_live), _stream())
+                            out.score_ptr(), out.item_ptr(), 2 * out.k, _p(n_users_live), 0, _stream())
     _lib.check(rc, 'trk_topk_merge')
     return out
 
 
-def topk_merge_received(recv, n_users, n_lists, k):
-    """Merge of the exchange receive buffer int32 [n_lists, n_users, 2k] (list l = the candidates rank l found for
-    THIS rank's user slice) -> PackedTopK [n_users, k]."""
+def topk_merge_received(recv, n_users, n_lists, k, dedup=False):
+    """Merge of int32 [n_lists, n_users, 2k] -> PackedTopK [n_users, k]: the exchange receive buffer (list l = the
+    candidates rank l found for THIS rank's user slice), or -- with dedup -- the per-taste results of a
+    mixture-of-tastes model (list t = the top-k of taste t; an item named by several tastes keeps its best score)."""
     lib = require_cuda()
     out = PackedTopK(n_users, k, recv.device)
     if n_users == 0:
         return out
     base = recv.data_ptr()
     rc = lib.trk_topk_merge(ctypes.c_void_p(base), ctypes.c_void_p(base + 4 * k), n_users, int(n_lists), int(k), int(k),
-                            2 * k, n_users * 2 * k, out.score_ptr(), out.item_ptr(), 2 * k, None, _stream())
+                            2 * k, n_users * 2 * k, out.score_ptr(), out.item_ptr(), 2 * k, None, 1 if dedup else 0,
+                            _stream())
     _lib.check(rc, 'trk_topk_merge')
     return out
 

@@ -517,17 +517,19 @@ class TensorRec(object):
     def _projected_biases(self, sparse_input, name, device):
         return kernels.project_biases(sparse_input.device_csr(device), self._var(name, device).reshape(-1))
 
-    def _tensor_path_ok(self):
+    def _tensor_path_ok(self, allow_tastes=False):
+        """Can the tcgen05 kernels evaluate this model?  allow_tastes: the fused top-k also covers n_tastes > 1 without
+        attention (one sweep per taste, then a de-duplicating merge: the prediction is the maximum over the tastes)."""
         if SCORE_PATH == 'exact':
             return False
         ok = (type(self.prediction_graph_factory) in (DotProductPredictionGraph, CosineSimilarityPredictionGraph)
-              and self.n_tastes == 1 and self.attention_graph_factory is None
+              and (self.n_tastes == 1 or allow_tastes) and self.attention_graph_factory is None
               and kernels.d_pad_for(self.n_components) <= 128)
         if SCORE_PATH == 'tensor' and not ok:
             raise RuntimeError('TENSORREC_B200_SCORE_PATH=tensor but this model cannot use the tcgen05 kernel')
         return ok
 
-    def _side_operands(self, side, sparse_in, device, for_filter=False):
+    def _side_operands(self, side, sparse_in, device, for_filter=False, taste=0):
         """One side ('user' or 'item') as kernels.SideOperands: split-fp16 operand + scale, projected biases and -- for
         the filter form of the fused top-k -- the row norms (users) / the global statistics (items), all from K1."""
         extra = 1 if type(self.prediction_graph_factory) is CosineSimilarityPredictionGraph else 0
@@ -538,7 +540,7 @@ class TensorRec(object):
         stats = norm = None
         if for_filter and not is_user:
             stats = torch.empty((3,), dtype=torch.float32, device=device)
-        out = self._represent(graph, sparse_in, n_features, 'user_0' if is_user else 'item', device, extra,
+        out = self._represent(graph, sparse_in, n_features, 'user_{}'.format(taste) if is_user else 'item', device, extra,
                               want_f32=False, split_d_pad=d_pad, want_norm=for_filter and is_user, stats=stats)
         split, scale = out[1], out[2]
         if for_filter and is_user:
@@ -760,7 +762,8 @@ class TensorRec(object):
             return TopK(np.zeros((0, k), np.int32), np.zeros((0, k), np.float32))
         from . import distributed
 
-        fused = self._tensor_path_ok() and k <= kernels.topk_max_k(kernels.d_pad_for(self.n_components)) and n_items > 0
+        fused = (self._tensor_path_ok(allow_tastes=True) and n_items > 0 and
+                 k <= kernels.topk_max_k(kernels.d_pad_for(self.n_components)))
         use_filter = fused and TOPK_PATH != 'exact' and k <= kernels.filter_max_k()
         info = self.last_topk_info = {'path': 'filter' if use_filter else ('exact3' if fused else 'dense+rank'),
                                       'fallback_rows': 0}
@@ -778,13 +781,25 @@ class TensorRec(object):
             blocks = [(u0, min(n_users, u0 + step), SparseInput(csr[u0:min(n_users, u0 + step)]))
                       for u0 in range(0, n_users, step)]
 
+        def run_taste(block_in, taste, force_exact):
+            users = self._side_operands('user', block_in, device, for_filter=use_filter and not force_exact, taste=taste)
+            if use_filter and not force_exact:
+                return kernels.topk_filter(users, items, k, item_id_offset=item_id_offset, fitems=fitems)
+            return kernels.topk_exact(users, items, k, item_id_offset=item_id_offset), None, 0
+
         def run_block(block_in, force_exact=False):
-            if fused:
-                users = self._side_operands('user', block_in, device, for_filter=use_filter and not force_exact)
-                if use_filter and not force_exact:
-                    return kernels.topk_filter(users, items, k, item_id_offset=item_id_offset, fitems=fitems)
-                return kernels.topk_exact(users, items, k, item_id_offset=item_id_offset), None, 0
-            return self._topk_from_dense(block_in, item_in, k, item_id_offset, device), None, 0
+            """-> (PackedTopK of the block, [(device counters | None, capacity)] of its sweeps)"""
+            if not fused:
+                return self._topk_from_dense(block_in, item_in, k, item_id_offset, device), [(None, 0)]
+            if self.n_tastes == 1:
+                top, cnt, cap = run_taste(block_in, 0, force_exact)
+                return top, [(cnt, cap)]
+            # mixture of tastes (no attention): prediction = max over tastes (recommendation_graphs.py:107), so the top-k
+            # lies in the union of the per-taste top-k lists: one fused sweep per taste, then a de-duplicating merge
+            per_taste = [run_taste(block_in, t, force_exact) for t in range(self.n_tastes)]
+            stacked = torch.stack([top.buf for top, _, _ in per_taste]).contiguous()          # [T, U_block, 2k]
+            merged = kernels.topk_merge_received(stacked, block_in.shape[0], self.n_tastes, k, dedup=True)
+            return merged, [(cnt, cap) for _, cnt, cap in per_taste]
 
         def exchange(top, u0, u1):
             if gather_group is None:
@@ -796,31 +811,31 @@ class TensorRec(object):
 
         results, counters, rows = [], [], []
         for (u0, u1, block_in) in blocks:
-            top, cnt, cap = run_block(block_in)
+            top, sweeps = run_block(block_in)
             top, user_rows = exchange(top, u0, u1)
             results.append(top)
-            counters.append((cnt, cap))
+            counters.append(sweeps)
             rows.append(user_rows)
 
-        # one synchronisation for the whole call: how many rows the certificate rejected per block (device counters);
+        # one synchronisation for the whole call: how many rows the certificate rejected per sweep (device counters);
         # a block with more rejected rows than the device-side fallback holds is re-run through the exact kernel
-        live = [c for c, _ in counters if c is not None]
+        live = [c for sweeps in counters for c, _ in sweeps if c is not None]
         if live:
-            counts = torch.stack([c[0] for c in live]).cpu().numpy().tolist()
-            counts = iter(counts)
+            counts = iter(torch.stack([c[0] for c in live]).cpu().numpy().tolist())
             overflow = []
-            for b, (c, cap) in enumerate(counters):
-                if c is None:
-                    continue
-                n_bad = next(counts)
-                info['fallback_rows'] += min(n_bad, cap)
-                if n_bad > cap:
-                    overflow.append(b)
+            for b, sweeps in enumerate(counters):
+                for c, cap in sweeps:
+                    if c is None:
+                        continue
+                    n_bad = next(counts)
+                    info['fallback_rows'] += min(n_bad, cap)
+                    if n_bad > cap and b not in overflow:
+                        overflow.append(b)
             if gather_group is not None:     # every rank must take the same decision: the exchange is collective
                 overflow = distributed.union_of_indices(overflow, len(blocks), gather_group, device)
             for b in overflow:
                 u0, u1, block_in = blocks[b]
-                top, _, _ = run_block(block_in, force_exact=True)
+                top, _ = run_block(block_in, force_exact=True)
                 results[b], rows[b] = exchange(top, u0, u1)
             info['overflow_blocks'] = len(overflow)
         info['user_rows'] = rows[0] if len(rows) == 1 else np.concatenate(rows)

@@ -16,7 +16,6 @@ WMRBLossGraph or BalancedWMRBLossGraph, one taste, no attention -- one Adam step
 Every other model family trains through the torch-autograd mirror of the reference's graph functions
 (TensorRec._training_losses); TENSORREC_B200_TRAIN_PATH=torch forces that path."""
 import ctypes
-import math
 import os
 
 import numpy as np
@@ -89,6 +88,7 @@ class WmrbStep(object):
             if seed is None else int(seed)
         self.bf16 = (TRAIN_DTYPE == 'bf16') if bf16 is None else bool(bf16)
         self.t = 0
+        self.beta_powers = (np.float32(1.0), np.float32(1.0))    # beta1^t, beta2^t as float32 variables (TensorFlow)
         self.moments = {}            # weight name -> (m, v)
         self.last = {}
         self.marks = None            # bench.py: list that receives (phase name, CUDA event) pairs of a step
@@ -196,7 +196,9 @@ class WmrbStep(object):
         self._mark('weight_gradients')
         # Adam
         self.t += 1
-        lr_t = learning_rate * math.sqrt(1.0 - ADAM_BETA2 ** self.t) / (1.0 - ADAM_BETA1 ** self.t)
+        f32 = np.float32
+        self.beta_powers = (f32(self.beta_powers[0] * f32(ADAM_BETA1)), f32(self.beta_powers[1] * f32(ADAM_BETA2)))
+        lr_t = float(f32(learning_rate) * np.sqrt(f32(1.0) - self.beta_powers[1]) / (f32(1.0) - self.beta_powers[0]))
         for name in names:
             w = ws[name]
             if name not in self.moments:

@@ -442,3 +442,34 @@ def test_streamed_predict_equals_one_shot(T, kind, tmp_path):
     assert seen == [(0, 200), (200, 400), (400, 600), (600, 700)]
     with pytest.raises(ValueError):
         model.predict(uf, itf, out=np.zeros((U, I + 1), np.float32))
+
+
+@pytest.mark.parametrize('integer', [True, False])
+def test_mixture_of_tastes_top_k_stays_on_the_fused_kernels(T, integer):
+    """n_tastes > 1 without attention: prediction = max over tastes, so predict_rank(k) = one fused sweep per taste + a
+    de-duplicating merge -- no [n_users, n_items] matrix (SURVEY a6 / VERDICT r1 'missing 3')."""
+    U, I, d, k, n_tastes = 300, 4000, 64, 10, 3
+    uf = H.tag_features(U, 200, 20, seed=1, integer=integer)
+    itf = H.tag_features(I, 200, 20, seed=2, integer=integer)
+    wus = [H.linear_weights(200, d, seed=10 + t, integer=integer) for t in range(n_tastes)]
+    wi = H.linear_weights(200, d, seed=4, integer=integer)
+    bu, bi = H.feature_biases(200, seed=5, integer=integer), H.feature_biases(200, seed=6, integer=integer)
+    model = T.TensorRec(n_components=d, n_tastes=n_tastes)
+    weights = {'linear_weights_item': wi, 'feature_biases_user': bu[:, None], 'feature_biases_item': bi[:, None]}
+    for t in range(n_tastes):
+        weights['linear_weights_user_%d' % t] = wus[t]
+    model.set_weights(weights)
+    top = model.predict_rank(uf, itf, k=k)
+    assert model.last_topk_info['path'] == 'filter'
+    scores = oracle.OracleModel(wus, wi, bu, bi).predict(uf, itf)
+    exp_i, exp_s = oracle.top_k_from_scores(scores, k)
+    if integer:
+        assert np.array_equal(top.items, exp_i) and np.array_equal(top.scores, exp_s)
+    else:
+        rows = np.arange(U)[:, None]
+        assert np.all(np.abs(top.scores - scores[rows, top.items]) <= 1e-5 * 40 + 2e-6)
+        assert (top.items != exp_i).mean() < 0.01
+        assert all(len(set(r)) == k for r in top.items)            # no item twice
+    # the dense API of the same model agrees with the oracle as before
+    if integer:
+        assert np.array_equal(model.predict(uf, itf), scores)
