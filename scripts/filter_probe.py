@@ -50,8 +50,39 @@ def run_filter():
                                 d_pad, A.k, block_bias_min=f.block_min)
 
 
+def timeit_cool(fn, n=5, pause=0.4):
+    """Single launches separated by idle time: the GPU is not at its power cap, the SM clock is near its maximum -- what a
+    30 ms kernel inside a short multi-GPU step sees (back-to-back launches settle at ~1.45 GHz under the 1 kW cap)."""
+    import time
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        time.sleep(pause)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
 pairs = A.users * float(A.items)
 print('shape %d users x %d items, d=%d' % (A.users, A.items, A.d))
+if os.environ.get('PROBE_COOL'):
+    print('single launches after idle (high clocks): full kernel %.2f ms' % timeit_cool(run_filter))
+    for mode in ('4', '1', '2', '6'):
+        os.environ['TRK_FILTER_DEBUG'] = mode
+        print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
+    os.environ['TRK_FILTER_DEBUG'] = '0'
+    os.environ['TRK_FILTER_NO_WARMSTART'] = '1'
+    print('  cool, no first-tile threshold: %.2f ms' % timeit_cool(run_filter))
+    os.environ.pop('TRK_FILTER_NO_WARMSTART')
+    for cl in ('1', '2'):
+        os.environ['TRK_FILTER_CLUSTER'] = cl
+        print('  cool, clusters of %s: %.2f ms' % (cl, timeit_cool(run_filter)))
+    os.environ.pop('TRK_FILTER_CLUSTER')
 ms = timeit(run_filter)
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
 os.environ['TRK_FILTER_NO_WARMSTART'] = '1'

@@ -139,9 +139,10 @@ def test_tastes_normalized_cosine_and_attention(T):
     assert np.all(np.abs(got - om.predict(uf, itf)) <= 3e-6)
     assert model.predict_user_representation(uf).shape == (3, 15, 10)
     assert np.array_equal(model.predict_rank(uf, itf), oracle.rank_predictions(got))
-    top = model.predict_rank(uf, itf, k=5)                       # n_tastes > 1: the non-fused top-k route
+    top = model.predict_rank(uf, itf, k=5)                       # n_tastes > 1: one fused sweep per taste + merge
+    assert model.last_topk_info['path'] == 'filter'
     exp_i, exp_s = oracle.top_k_from_scores(got, 5)
-    assert np.array_equal(top.items, exp_i) and np.array_equal(top.scores, exp_s)
+    assert np.array_equal(top.items, exp_i) and np.all(np.abs(top.scores - exp_s) <= 3e-6)
 
     model, om = build(T, uf, itf, d=10, n_tastes=3, attention=True)
     got = model.predict(uf, itf)
