@@ -295,11 +295,30 @@ def run_b200(args):
     n_users, n_items, d, k = args.users, args.items, args.d, args.k
     d_pad = kernels.d_pad_for(d)
     # item axis sharded over ranks; --emulate-shards N times ONE shard of N on one GPU (development aid)
-    n_shards = args.emulate_shards if (world == 1 and args.emulate_shards > 1) else world
-    lo, hi = shard_bounds(n_items, n_shards, rank if world > 1 else 0)
+    # Layout of the ranks: item_shards ranks form one ITEM GROUP (they split the item axis and exchange their per-shard
+    # top-k); world / item_shards such groups split the users.  Default item_shards = world: the item axis sharded over all
+    # GPUs (BASELINE north_star); --item-shards S < world is the grid form (users are independent: no collective
+    # between groups).
+    item_shards = world if args.item_shards in (None, 0) else int(args.item_shards)
+    if world % item_shards != 0:
+        raise SystemExit('--item-shards %d does not divide the %d ranks' % (item_shards, world))
+    n_groups = world // item_shards
+    user_group, item_rank = rank // item_shards, rank % item_shards
+    item_group = None
+    if world > 1:
+        for g in range(n_groups):
+            grp = dist.new_group(list(range(g * item_shards, (g + 1) * item_shards)))
+            if g == user_group:
+                item_group = grp
+    n_shards = args.emulate_shards if (world == 1 and args.emulate_shards > 1) else item_shards
+    lo, hi = shard_bounds(n_items, n_shards, item_rank if world > 1 else 0)
     itf_local = itf[lo:hi]
     n_local = hi - lo
-    u_lo, u_hi = shard_bounds(n_users, world, rank)     # the user slice whose final answer this rank forms
+    g_lo, g_hi = shard_bounds(n_users, n_groups, user_group)       # the users of this rank's group
+    uf_all, n_users_all = uf, n_users
+    uf, n_users = uf[g_lo:g_hi], g_hi - g_lo                       # from here on: the group's users
+    s_lo, s_hi = shard_bounds(n_users, item_shards, item_rank)     # ... of which this rank forms the final answer for
+    u_lo, u_hi = g_lo + s_lo, g_lo + s_hi                          # (global user ids)
 
     def barrier():
         if world > 1:
@@ -365,10 +384,10 @@ def run_b200(args):
             top = kernels.topk_merge(cs, ci, k)
             mark()
         mark()
-        if world > 1:
-            recv, _ = exchange_rows(top.buf)
+        if item_shards > 1:
+            recv, _ = exchange_rows(top.buf, item_group)
             mark()
-            top = kernels.topk_merge_received(recv, u_hi - u_lo, world, k)
+            top = kernels.topk_merge_received(recv, u_hi - u_lo, item_shards, k)
         else:
             mark()
         mark()
@@ -400,7 +419,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     # whole job: all users x all items; --emulate-shards times ONE shard's pairs (development aid, not a bench value)
-    pairs = n_users * float(n_local if (world == 1 and n_shards > 1) else n_items)
+    pairs = n_users_all * float(n_local if (world == 1 and n_shards > 1) else n_items)
     value = pairs / (ms_step * 1e-3)
     # per-phase device time of this rank (means over the timed steps)
     phase_ms = np.zeros(len(PHASES))
@@ -423,9 +442,9 @@ def run_b200(args):
     if use_filter:
         fallback_rows = int(last['counters'][0])
         bad_ids = torch.nonzero(last['bad'], as_tuple=True)[0]
-        bad_ids = bad_ids[(bad_ids >= u_lo) & (bad_ids < u_hi)][:args.parity_fallback_rows]
-        fallback_ids = bad_ids.cpu().numpy()
-        fallback_items = out.items[bad_ids - u_lo].cpu().numpy()
+        bad_ids = bad_ids[(bad_ids >= s_lo) & (bad_ids < s_hi)][:args.parity_fallback_rows]      # rows within the group
+        fallback_ids = bad_ids.cpu().numpy() + g_lo                                               # global user ids
+        fallback_items = out.items[bad_ids - s_lo].cpu().numpy()
 
     # ---- e2e: the public API with host buffers ----------------------------------------------------------
     def pinned_csr(m):
@@ -443,7 +462,7 @@ def run_b200(args):
                        'feature_biases_item': bi[:, None]})
     uf_host, _keep_u = pinned_csr(uf)
     itf_host, _keep_i = pinned_csr(itf_local)
-    group = dist.group.WORLD if world > 1 else None
+    group = item_group if item_shards > 1 else None
 
     def e2e_step():
         return model.predict_top_k(uf_host, itf_host, k, item_id_offset=lo, gather_group=group, gather='slice',
@@ -470,7 +489,7 @@ def run_b200(args):
     e2e_ms_step = float(t.item()) / args.steps
     e2e_value = pairs / (e2e_ms_step * 1e-3)
     h2d = 4 * (uf.nnz * 2 + uf.shape[0] + 1 + itf_local.nnz * 2 + itf_local.shape[0] + 1)
-    d2h = n_users * k * 8      # whole job: every rank reads back the top-k of ITS user slice
+    d2h = n_users_all * k * 8  # whole job: every rank reads back the top-k of ITS user slice
     same = bool(np.array_equal(top.items[:4], top_items_value))
 
     if rank != 0:
@@ -491,7 +510,7 @@ def run_b200(args):
     k1_gbs = k1_survey_bytes / (k1u_ms * 1e-3) / 1e9
 
     cores = os.cpu_count() or 1
-    cpu_value, cpu_desc, cpu_s, cpu_top = cpu_oracle_leg(uf, itf, wu, wi, bu, bi, k, args.cpu_budget, cores,
+    cpu_value, cpu_desc, cpu_s, cpu_top = cpu_oracle_leg(uf_all, itf, wu, wi, bu, bi, k, args.cpu_budget, cores,
                                                          cosine=cosine)
     # parity at the full item count: the reference-semantics ranking (oracle, CPU) of the first users of this rank's
     # slice AND of the rows the certificate rejected in the last step, against the GPU top-k of the same users; only
@@ -499,7 +518,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     rows = np.concatenate([np.arange(u_lo, u_lo + n_check), fallback_ids]).astype(np.int64)
     emulating = world == 1 and n_shards > 1
-    exp, _, _ = oracle_topk_rows(uf, itf_local if emulating else itf, wu, wi, bu, bi, rows, k, cosine=cosine)
+    exp, _, _ = oracle_topk_rows(uf_all, itf_local if emulating else itf, wu, wi, bu, bi, rows, k, cosine=cosine)
     exp = exp + (lo if emulating else 0)
     got = np.concatenate([top_items_check, fallback_items]) if len(fallback_ids) else top_items_check
     agree = float((exp == got).mean()) if len(rows) else None
@@ -522,8 +541,10 @@ def run_b200(args):
                   if use_filter else 'f32 (3 x fp16 split-product tcgen05 passes, fp32 accumulate)'),
         'data': 'synthetic',
         'config': {'workload': workload_string(args),
-                   'parallelism': ('item-sharded x%d: 1 NCCL all-to-all of the per-shard top-k, each rank merges its '
-                                   'user slice' % world) if world > 1 else 'single GPU',
+                   'parallelism': ('item axis sharded x%d%s: 1 NCCL all-to-all of the per-shard top-k per item group, each '
+                                   'rank merges its user slice'
+                                   % (item_shards, '' if n_groups == 1 else ' x %d user groups' % n_groups))
+                   if world > 1 else 'single GPU',
                    'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
                    'fallback_rows_last_step': fallback_rows, 'scores': args.scores,
                    'fallback_overflow_whole_batch_exact': bool(last_overflow),
@@ -921,6 +942,9 @@ def main():
     ap.add_argument('--emulate-shards', type=int, default=1,
                     help='development aid (1 GPU): time the work of ONE item shard out of this many, no exchange')
     ap.add_argument('--no-clocks', action='store_true', help='do not sample nvidia-smi during the timed region')
+    ap.add_argument('--item-shards', type=int, default=None,
+                    help='ranks per item group (default: all ranks = the item axis sharded over every GPU); a divisor of the '
+                         'rank count gives the grid form: item_shards x (ranks / item_shards) user groups')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads of the default run')
     ap.add_argument('--n-sampled', type=int, default=64, help='--workload train: n_sampled_items')
     ap.add_argument('--train-dtype', default='bf16', choices=['bf16', 'f32'], help='--workload train: representations')

@@ -259,14 +259,17 @@ __device__ __forceinline__ void compact_rows(unsigned rows, uint32_t buf_row_add
 // formed.  The hitting lanes then append their survivors (approximate score + original item id) and rows whose buffer
 // passed half full are compacted by the whole warp.
 // (Voting once per 32 columns instead measured 7-11 % SLOWER at 1M x 1M x d128; the 16-column granularity stays.)
-__device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
-  float amax = fmaxf(fmaxf(__uint_as_float(acc[0]), __uint_as_float(acc[1])),
-                     fmaxf(__uint_as_float(acc[2]), __uint_as_float(acc[3])));
+// maximum of 16 columns; g[q] = maximum of columns [4q, 4q + 4) (the slow path looks only into the groups that pass)
+__device__ __forceinline__ float acc_max_16(const uint32_t* acc, float (&g)[4]) {
 #pragma unroll
-  for (int q = 1; q < 4; ++q)
-    amax = fmaxf(amax, fmaxf(fmaxf(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])),
-                             fmaxf(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]))));
-  return amax;
+  for (int q = 0; q < 4; ++q)
+    g[q] = fmaxf(fmaxf(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1])),
+                 fmaxf(__uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3])));
+  return fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+}
+__device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
+  float g[4];
+  return acc_max_16(acc, g);
 }
 
 // slow path of 16 columns: the lanes whose bound passed append every column that passes the same bound as a raw
@@ -297,18 +300,24 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t 
   }
 }
 
-// Bit mask of the columns of acc[0, 16) whose admission bound passes: 16 independent compares and an OR tree (a serial
-// `mask |= ...` chain put ~80 cycles of dependent latency into every slow-path entry).
-__device__ __forceinline__ uint32_t pass_mask_16(const uint32_t* acc, float bmax_scaled, float tau) {
-  uint32_t b[16];
+// Bit mask of the columns of acc[0, 16) whose admission bound passes.  g[q] = maximum of columns [4q, 4q + 4) from the
+// hot loop: only a group whose maximum passes is looked into (x -> x + bmax is monotonic), so the usual single hit
+// costs 4 + 4 compares instead of 16; independent compares, OR'ed pairwise (a serial `mask |= ...` chain put ~80 cycles
+// of dependent latency into every slow-path entry).
+__device__ __forceinline__ uint32_t pass_mask_16(const uint32_t* acc, const float (&g)[4], float bmax_scaled,
+                                                 float tau) {
+  uint32_t mask = 0;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) b[j] = (__uint_as_float(acc[j]) + bmax_scaled > tau) ? (1u << j) : 0u;
-#pragma unroll
-  for (int s = 8; s > 0; s >>= 1) {
-#pragma unroll
-    for (int j = 0; j < s; ++j) b[j] |= b[j + s];
+  for (int q = 0; q < 4; ++q) {
+    if (g[q] + bmax_scaled > tau) {
+      const uint32_t b0 = (__uint_as_float(acc[4 * q + 0]) + bmax_scaled > tau) ? (1u << (4 * q + 0)) : 0u;
+      const uint32_t b1 = (__uint_as_float(acc[4 * q + 1]) + bmax_scaled > tau) ? (1u << (4 * q + 1)) : 0u;
+      const uint32_t b2 = (__uint_as_float(acc[4 * q + 2]) + bmax_scaled > tau) ? (1u << (4 * q + 2)) : 0u;
+      const uint32_t b3 = (__uint_as_float(acc[4 * q + 3]) + bmax_scaled > tau) ? (1u << (4 * q + 3)) : 0u;
+      mask |= (b0 | b1) | (b2 | b3);
+    }
   }
-  return b[0];
+  return mask;
 }
 // Appends the columns of `mask` (a 16-column half, its maximum `amax` known from the hot loop).  One passing column -- the
 // normal case -- IS the maximum of its half (x -> x + bmax is monotonic, so the largest accumulator passes whenever any
@@ -339,12 +348,13 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
                                           float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
                                           int lane, int k) {
-  const float a0 = acc_max_16(acc), a1 = acc_max_16(acc + 16);
+  float g0[4], g1[4];
+  const float a0 = acc_max_16(acc, g0), a1 = acc_max_16(acc + 16, g1);
   const bool h0 = a0 + bmax_scaled > tau, h1 = a1 + bmax_scaled > tau;
   if (__any_sync(0xffffffffu, h0 || h1)) {
     uint32_t lo = 0, hi = 0;
-    if (h0) lo = pass_mask_16(acc, bmax_scaled, tau);
-    if (h1) hi = pass_mask_16(acc + 16, bmax_scaled, tau);
+    if (h0) lo = pass_mask_16(acc, g0, bmax_scaled, tau);
+    if (h1) hi = pass_mask_16(acc + 16, g1, bmax_scaled, tau);
     if (__ballot_sync(0xffffffffu, cnt + __popc(lo) + __popc(hi) > kBufEntries) == 0u) {
       if (lo != 0u) append_16(acc, lo, a0, pos_base, buf_row_addr, cnt);
       if (hi != 0u) append_16(acc + 16, hi, a1, pos_base + 16, buf_row_addr, cnt);
