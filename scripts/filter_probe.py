@@ -76,9 +76,10 @@ if os.environ.get('PROBE_COOL'):
         os.environ['TRK_FILTER_DEBUG'] = mode
         print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
     os.environ['TRK_FILTER_DEBUG'] = '0'
-    os.environ['TRK_FILTER_NO_WARMSTART'] = '1'
-    print('  cool, no first-tile threshold: %.2f ms' % timeit_cool(run_filter))
-    os.environ.pop('TRK_FILTER_NO_WARMSTART')
+    for trig in ('32', '26', '22', '20', '18', '16', '14'):
+        os.environ['TRK_FILTER_TILE_END_TRIGGER'] = trig
+        print('  cool, tile-end compaction above %s entries: %.2f ms' % (trig, timeit_cool(run_filter)))
+    os.environ.pop('TRK_FILTER_TILE_END_TRIGGER')
     for cl in ('1', '2'):
         os.environ['TRK_FILTER_CLUSTER'] = cl
         print('  cool, clusters of %s: %.2f ms' % (cl, timeit_cool(run_filter)))

@@ -75,6 +75,7 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
+  int32_t tile_end_trigger;    // rows holding more entries than this are compacted at the END of a tile (see the epilogue)
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
   float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
@@ -693,6 +694,16 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + slot);
+        // A compaction waits one L2 round trip for the biases / item ids of its new entries (almost all of shared memory
+        // is carved out: there is no L1 to speak of) -- ~0.8 us during which, in the middle of a tile, the warp's 32 rows
+        // stand still AND their accumulator slot stays occupied: the admission path cost ~10 ms of a 31 ms sweep of a
+        // 125K-item shard, the same at 1.45 and at 1.9 GHz (profiles/probe_r2_v9_filter_shard8_cool.txt).  So rows whose
+        // buffer is filling up are compacted HERE, after the slot has gone back to the MMA warp: the round trip overlaps
+        // the MMAs of this group's next accumulator.  The mid-tile path remains for a row that overflows inside a tile.
+        if (p.tile_end_trigger < kBufEntries && p.debug_mode == 0) {
+          const unsigned early = __ballot_sync(0xffffffffu, cnt > p.tile_end_trigger);
+          compact_rows(early, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+        }
         slot += 2;                          // q += 2
         if (slot >= kFAccSlots) {
           slot -= kFAccSlots;
@@ -919,6 +930,11 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
   p.n_user_pairs = static_cast<int32_t>(ceil_div(n_users, 2 * kFBlockM));
   p.item_id_offset = item_id_offset;
+  {
+    const char* env = getenv("TRK_FILTER_TILE_END_TRIGGER");   // probe knob; kBufEntries (32) switches the tile-end pass off
+    p.tile_end_trigger = env != nullptr ? atoi(env) : 20;
+    if (p.tile_end_trigger < k) p.tile_end_trigger = k;
+  }
   p.cand_score = cand_score;
   p.cand_item = cand_item;
   p.row_theta = row_theta;
