@@ -76,16 +76,29 @@ if os.environ.get('PROBE_COOL'):
         os.environ['TRK_FILTER_DEBUG'] = mode
         print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
     os.environ['TRK_FILTER_DEBUG'] = '0'
-    for trig in ('32', '26', '22', '20', '18', '16', '14'):
-        os.environ['TRK_FILTER_TILE_END_TRIGGER'] = trig
-        print('  cool, tile-end compaction above %s entries: %.2f ms' % (trig, timeit_cool(run_filter)))
-    os.environ.pop('TRK_FILTER_TILE_END_TRIGGER')
+    for roles in ('0', '1'):
+        os.environ['TRK_FILTER_ROLES_HIGH'] = roles
+        print('  cool, MMA/TMA warps highest = %s: full %.2f ms' % (roles, timeit_cool(run_filter)))
+        for mode in ('4', '6'):
+            os.environ['TRK_FILTER_DEBUG'] = mode
+            print('    debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
+        os.environ['TRK_FILTER_DEBUG'] = '0'
+        for trig in ('32', '26'):
+            os.environ['TRK_FILTER_TILE_END_TRIGGER'] = trig
+            print('    tile-end compaction above %s entries: %.2f ms' % (trig, timeit_cool(run_filter)))
+        os.environ.pop('TRK_FILTER_TILE_END_TRIGGER')
+    os.environ.pop('TRK_FILTER_ROLES_HIGH')
     for cl in ('1', '2'):
         os.environ['TRK_FILTER_CLUSTER'] = cl
         print('  cool, clusters of %s: %.2f ms' % (cl, timeit_cool(run_filter)))
     os.environ.pop('TRK_FILTER_CLUSTER')
 ms = timeit(run_filter)
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+os.environ['TRK_FILTER_ROLES_HIGH'] = '0'
+print('filter kernel, round-1 warp order: %.2f ms' % timeit(run_filter))
+os.environ.pop('TRK_FILTER_ROLES_HIGH')
+if os.environ.get('PROBE_SHORT'):
+    sys.exit(0)
 os.environ['TRK_FILTER_NO_WARMSTART'] = '1'
 print('filter kernel, no threshold prologue at all: %.2f ms' % timeit(run_filter))
 os.environ.pop('TRK_FILTER_NO_WARMSTART')
