@@ -76,9 +76,6 @@ if os.environ.get('PROBE_COOL'):
         os.environ['TRK_FILTER_DEBUG'] = mode
         print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
     os.environ['TRK_FILTER_DEBUG'] = '0'
-    os.environ['TRK_FILTER_NO_EARLY_RELEASE'] = '1'
-    print('  cool, slot released only after the last chunk is filtered: %.2f ms' % timeit_cool(run_filter))
-    os.environ.pop('TRK_FILTER_NO_EARLY_RELEASE')
     for trig in ('32', '26'):
         os.environ['TRK_FILTER_TILE_END_TRIGGER'] = trig
         print('  cool, tile-end compaction above %s entries: %.2f ms' % (trig, timeit_cool(run_filter)))
@@ -89,9 +86,6 @@ if os.environ.get('PROBE_COOL'):
     os.environ.pop('TRK_FILTER_CLUSTER')
 ms = timeit(run_filter)
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
-os.environ['TRK_FILTER_NO_EARLY_RELEASE'] = '1'
-print('filter kernel, slot released only after the last chunk is filtered: %.2f ms' % timeit(run_filter))
-os.environ.pop('TRK_FILTER_NO_EARLY_RELEASE')
 if os.environ.get('PROBE_SHORT'):
     sys.exit(0)
 os.environ['TRK_FILTER_NO_WARMSTART'] = '1'

@@ -75,7 +75,6 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
-  int32_t early_release;       // 1: the accumulator slot goes back to the MMA warp as soon as its last chunk is in registers
   int32_t tile_end_trigger;    // rows holding more entries than this are compacted at the END of a tile (see the epilogue)
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
@@ -631,7 +630,6 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tcgen05_fence_after();
         const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
-        bool released = false;
         if (t == t0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
           const float bmin = __ldg(p.block_bias_min + t0);   // the same for the whole CTA: warp-uniform branch
           if (bmin > kNegInf) {
@@ -686,33 +684,25 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
           filter_32(ra, pos0 + ch * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
                     n_res, lane, p.k);
           tmem_ld_wait();
-          if (ch + 2 < kFBlockN / 32) {
-            tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          } else if (p.early_release) {
-            // the last chunk is in registers: the slot is free for the MMA warp while that chunk is still being filtered
-            // (a slow-path entry in it no longer holds the accumulator)
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + slot);
-            released = true;
-          }
+          if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
           filter_32(rb, pos0 + (ch + 1) * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
                     cnt, n_res, lane, p.k);
           tmem_ld_wait();
         }
       drained:
         // accumulator and bias slot drained
-        if (!released) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + slot);
-        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + slot);
         // A compaction waits one L2 round trip for the biases / item ids of its new entries (almost all of shared memory
         // is carved out: there is no L1 to speak of) -- ~0.8 us during which, in the middle of a tile, the warp's 32 rows
         // stand still AND their accumulator slot stays occupied: the admission path cost ~10 ms of a 31 ms sweep of a
         // 125K-item shard, the same at 1.45 and at 1.9 GHz (profiles/probe_r2_v9_filter_shard8_cool.txt).  So rows whose
         // buffer is filling up are compacted HERE, after the slot has gone back to the MMA warp: the round trip overlaps
-        // the MMAs of this group's next accumulator.  The mid-tile path remains for a row that overflows inside a tile.
+        // the MMAs of this group's next accumulator (-1.5 ms of 32 at the shard with the trigger at 26 of 32 entries,
+        // profiles/probe_r2_v10_filter_shard8_tile_end_trigger.txt).  The mid-tile path remains for a row that overflows
+        // inside a tile.  (Measured and not kept: releasing the slot before the last chunk is filtered, and giving the
+        // MMA / TMA warps the highest warp ids -- both neutral: the epilogue warps' own time per tile is the limit.)
         if (p.tile_end_trigger < kBufEntries && p.debug_mode == 0) {
           const unsigned early = __ballot_sync(0xffffffffu, cnt > p.tile_end_trigger);
           compact_rows(early, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
@@ -947,7 +937,6 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     const char* env = getenv("TRK_FILTER_TILE_END_TRIGGER");   // probe knob; kBufEntries (32) switches the tile-end pass off
     p.tile_end_trigger = env != nullptr ? atoi(env) : 26;
     if (p.tile_end_trigger < kKeepMax + 2) p.tile_end_trigger = kKeepMax + 2;   // (a compaction leaves up to kKeepMax)
-    p.early_release = getenv("TRK_FILTER_NO_EARLY_RELEASE") != nullptr ? 0 : 1;
   }
   p.cand_score = cand_score;
   p.cand_item = cand_item;
