@@ -90,7 +90,12 @@ def make_problem(args):
         uf = indicator_csr(args.users, seed=0)
         itf = indicator_csr(args.items, seed=1)
     rng = np.random.default_rng(4)
-    if scores == 'ties':
+    if scores == 'const':
+        wu = np.zeros((uf.shape[1], args.d), dtype=np.float32)
+        wi = np.zeros((itf.shape[1], args.d), dtype=np.float32)
+        bu = np.zeros(uf.shape[1], dtype=np.float32)
+        bi = np.zeros(itf.shape[1], dtype=np.float32)
+    elif scores == 'ties':
         wu = rng.integers(-2, 3, size=(uf.shape[1], args.d)).astype(np.float32)
         wi = rng.integers(-2, 3, size=(itf.shape[1], args.d)).astype(np.float32)
         bu = rng.integers(-3, 4, size=uf.shape[1]).astype(np.float32)
@@ -246,7 +251,8 @@ def workload_string(args):
     return ('predict_rank top-%d, %d users x %d items, d=%d, indicator-regime features, LinearRepr x DotProduct, biased '
             '(BASELINE configs[4] shape at the size the metric is quoted on; SURVEY C5)%s'
             % (args.k, args.users, args.items, args.d,
-               '' if scores == 'iid' else '; INTEGER-valued weights and biases: massive exact ties'))
+               {'iid': '', 'ties': '; INTEGER-valued weights and biases: massive exact ties',
+                'const': '; ALL weights and biases zero: every score equal, every row rejected by the certificate'}[scores]))
 
 
 PHASES = ['k1_users', 'items_prep', 'filter', 'rescore', 'fallback', 'exchange', 'merge']
@@ -931,7 +937,7 @@ def main():
     ap.add_argument('--k', type=int, default=10)
     ap.add_argument('--workload', default='topk', choices=['topk', 'dense', 'ranks', 'train'])
     ap.add_argument('--topk-path', default='filter', choices=['filter', 'exact'])
-    ap.add_argument('--scores', default='iid', choices=['iid', 'ties', 'c3'],
+    ap.add_argument('--scores', default='iid', choices=['iid', 'ties', 'c3', 'const'],
                     help='score distribution of the top-k workload: continuous (headline), integer-valued (massive ties), '
                          'or MovieLens-shaped features with cosine prediction')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
