@@ -72,7 +72,7 @@ pairs = A.users * float(A.items)
 print('shape %d users x %d items, d=%d' % (A.users, A.items, A.d))
 if os.environ.get('PROBE_COOL'):
     print('single launches after idle (high clocks): full kernel %.2f ms' % timeit_cool(run_filter))
-    for mode in ('4', '1', '2', '6'):
+    for mode in ('9', '4', '1', '2', '6'):
         os.environ['TRK_FILTER_DEBUG'] = mode
         print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
     os.environ['TRK_FILTER_DEBUG'] = '0'
@@ -86,6 +86,10 @@ if os.environ.get('PROBE_COOL'):
     os.environ.pop('TRK_FILTER_CLUSTER')
 ms = timeit(run_filter)
 print('filter kernel: %.2f ms  %.3e pairs/s  %.0f TFLOP/s' % (ms, pairs / ms * 1e3, 2 * pairs * A.d / ms / 1e9))
+for trig in ('32', '26', '22'):
+    os.environ['TRK_FILTER_TILE_END_TRIGGER'] = trig
+    print('filter kernel, tile-end compaction above %s entries: %.2f ms' % (trig, timeit(run_filter)))
+os.environ.pop('TRK_FILTER_TILE_END_TRIGGER')
 if os.environ.get('PROBE_SHORT'):
     sys.exit(0)
 os.environ['TRK_FILTER_NO_WARMSTART'] = '1'

@@ -53,6 +53,7 @@ constexpr int kFilterMaxK = 12;
 constexpr float kMarginFactor = 1.5f * 0.0009765625f;   // 1.5 * 2^-10
 constexpr float kBiasUlps = 4.0f * 1.1920929e-7f;        // 4 ulp(1): rounding of (dot + ub) + ib
 constexpr float kThetaMargins = 2.25f;                   // theta = a_k - 2.25 m  (> 2 m is what the proof needs)
+constexpr int kGiveUpOverflows = 8;   // a row whose compactions overflow this often is handed to the exact kernel
 
 struct FilterParams {
   const __half* user_split;    // [n_users, 2 d_pad] hi | lo; the filter reads the hi half
@@ -173,9 +174,14 @@ __device__ __forceinline__ RowFetch compact_fetch(uint32_t buf_row_addr, int lan
   }
   return f;
 }
+// n_ovf counts the compactions of this lane's row that found more than kKeepMax entries within the bound of the k-th
+// best.  Once in a while that is harmless (the surplus is remembered in drop_max).  A row where it keeps happening holds
+// massive near-ties (all-equal scores in the limit: EVERY column passes, every chunk takes the slow path and the sweep of
+// 1M x 1M took 43 s instead of 0.2): after kGiveUpOverflows of them the row stops admitting (tau = +inf) and is marked
+// uncertifiable (drop_max = +inf), i.e. it goes through the exact kernel -- where a tie-heavy row belongs anyway.
 __device__ __forceinline__ void compact_finish(const RowFetch& f, int lane, int src, int k, int& cnt, int& n_res,
-                                               float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
-                                               float inv_c, const AdmitCtx& ctx) {
+                                               float& theta, float& tau, float& drop_max, int& n_ovf, float m3,
+                                               float ubias, float c, float inv_c, const AdmitCtx& ctx) {
   const float kNegInf = -__int_as_float(0x7f800000);
   const int n = f.n;
   const uint32_t addr = f.addr;
@@ -222,7 +228,10 @@ __device__ __forceinline__ void compact_finish(const RowFetch& f, int lane, int 
   if (lane == src) {
     cnt = n_keep;
     n_res = n_keep;
-    if (ovf) drop_max = fmaxf(drop_max, first_dropped);
+    if (ovf) {
+      drop_max = fmaxf(drop_max, first_dropped);
+      n_ovf += 1;
+    }
     if (have_k) {
       theta = floor_s;
       // admission test runs on v = acc + bias/c; move theta there and leave a few ulps of slack (extra survivors are
@@ -230,13 +239,17 @@ __device__ __forceinline__ void compact_finish(const RowFetch& f, int lane, int 
       const float t = (theta - ubias) * inv_c;
       tau = t - 8.0f * 1.1920929e-7f * fabsf(t) - 1e-30f;
     }
+    if (n_ovf >= kGiveUpOverflows) {
+      tau = __int_as_float(0x7f800000);
+      drop_max = __int_as_float(0x7f800000);
+    }
   }
   __syncwarp();
 }
 // compacts every row of `rows` (bit = lane), the lookups of the next row in flight while the current one is sorted
 __device__ __forceinline__ void compact_rows(unsigned rows, uint32_t buf_row_addr, int lane, int k, int& cnt, int& n_res,
-                                             float& theta, float& tau, float& drop_max, float m3, float ubias, float c,
-                                             float inv_c, const AdmitCtx& ctx) {
+                                             float& theta, float& tau, float& drop_max, int& n_ovf, float m3,
+                                             float ubias, float c, float inv_c, const AdmitCtx& ctx) {
   if (rows == 0u) return;
   int src = __ffs(rows) - 1;
   rows &= rows - 1;
@@ -246,7 +259,7 @@ __device__ __forceinline__ void compact_rows(unsigned rows, uint32_t buf_row_add
     rows &= rows - 1;     // (0 stays 0)
     RowFetch ahead = cur;
     if (nxt >= 0) ahead = compact_fetch(buf_row_addr, lane, nxt, cnt, n_res, ctx);
-    compact_finish(cur, lane, src, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+    compact_finish(cur, lane, src, k, cnt, n_res, theta, tau, drop_max, n_ovf, m3, ubias, c, inv_c, ctx);
     if (nxt < 0) break;
     cur = ahead;
     src = nxt;
@@ -280,8 +293,8 @@ __device__ __forceinline__ float acc_max_16(const uint32_t* acc) {
 // Called warp-uniformly.
 __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t pos_base, float bmax_scaled,
                                          const AdmitCtx& ctx, float c, float inv_c, float ubias, float& tau,
-                                         float& theta, float& drop_max, float m3, uint32_t buf_row_addr, int& cnt,
-                                         int& n_res, int lane, int k) {
+                                         float& theta, float& drop_max, int& n_ovf, float m3, uint32_t buf_row_addr,
+                                         int& cnt, int& n_res, int lane, int k) {
   uint32_t pass = 0;
   if (hit) {
 #pragma unroll
@@ -289,8 +302,8 @@ __device__ __forceinline__ void admit_16(const uint32_t* acc, bool hit, int32_t 
   }
   __syncwarp();   // earlier appends of every lane are visible to the lanes that may now compact its row
   const unsigned need = __ballot_sync(0xffffffffu, cnt + __popc(pass) > kBufEntries);
-  compact_rows(need, buf_row_addr, lane, k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
-  if (pass != 0) {   // cnt + popc(pass) <= kBufEntries holds here (a compaction leaves at most kKeepMax = 16)
+  compact_rows(need, buf_row_addr, lane, k, cnt, n_res, theta, tau, drop_max, n_ovf, m3, ubias, c, inv_c, ctx);
+  if (pass != 0 && n_ovf < kGiveUpOverflows) {   // (a row that has just given up appends nothing more)   // cnt + popc(pass) <= kBufEntries holds here (a compaction leaves at most kKeepMax = 16)
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if ((pass >> j) & 1u) {
@@ -347,8 +360,8 @@ __device__ __forceinline__ void append_16(const uint32_t* acc, uint32_t mask, fl
 // compactions).
 __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base, float bmax_scaled, const AdmitCtx& ctx,
                                           float c, float inv_c, float ubias, float& tau, float& theta,
-                                          float& drop_max, float m3, uint32_t buf_row_addr, int& cnt, int& n_res,
-                                          int lane, int k) {
+                                          float& drop_max, int& n_ovf, float m3, uint32_t buf_row_addr, int& cnt,
+                                          int& n_res, int lane, int k) {
   float g0[4], g1[4];
   const float a0 = acc_max_16(acc, g0), a1 = acc_max_16(acc + 16, g1);
   const bool h0 = a0 + bmax_scaled > tau, h1 = a1 + bmax_scaled > tau;
@@ -360,10 +373,10 @@ __device__ __forceinline__ void filter_32(const uint32_t* acc, int32_t pos_base,
       if (lo != 0u) append_16(acc, lo, a0, pos_base, buf_row_addr, cnt);
       if (hi != 0u) append_16(acc + 16, hi, a1, pos_base + 16, buf_row_addr, cnt);
     } else {
-      admit_16(acc, h0, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt, n_res,
-               lane, k);
-      admit_16(acc + 16, h1, pos_base + 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
-               cnt, n_res, lane, k);
+      admit_16(acc, h0, pos_base, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3, buf_row_addr, cnt,
+               n_res, lane, k);
+      admit_16(acc + 16, h1, pos_base + 16, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3,
+               buf_row_addr, cnt, n_res, lane, k);
     }
   }
 }
@@ -596,7 +609,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       // error bound of one approximate score: operand rounding + the fp32 rounding of the two bias adds
       const float m3 = kThetaMargins * (kMarginFactor * unorm * max_item_norm + kBiasUlps * (fabsf(ubias) + max_item_bias));
       float tau = p.debug_mode == 4 ? -kNegInf : kNegInf, theta = kNegInf;   // 4: timing experiment, nothing admitted
-      int cnt = 0, n_res = 0;
+      int cnt = 0, n_res = 0, n_ovf = 0;
       float drop_max = kNegInf;
       uint32_t ra[32], rb[32];
 
@@ -630,7 +643,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tcgen05_fence_after();
         const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
-        if (t == t0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
+        if (t == t0 && p.block_bias_min != nullptr && (p.debug_mode == 0 || p.debug_mode == 9)) {
           const float bmin = __ldg(p.block_bias_min + t0);   // the same for the whole CTA: warp-uniform branch
           if (bmin > kNegInf) {
             float g[16];
@@ -679,14 +692,14 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tmem_ld_32x32b_x32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll 1
-        for (int ch = 0; ch < kFBlockN / 32; ch += 2) {
+        for (int ch = 0; ch < (p.debug_mode == 9 ? 2 : kFBlockN / 32); ch += 2) {   // 9: timing experiment, half the columns
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
-          filter_32(ra, pos0 + ch * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr, cnt,
-                    n_res, lane, p.k);
-          tmem_ld_wait();
-          if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-          filter_32(rb, pos0 + (ch + 1) * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, m3, buf_row_addr,
+          filter_32(ra, pos0 + ch * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3, buf_row_addr,
                     cnt, n_res, lane, p.k);
+          tmem_ld_wait();
+          if (ch + 2 < (p.debug_mode == 9 ? 2 : kFBlockN / 32)) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
+          filter_32(rb, pos0 + (ch + 1) * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3,
+                    buf_row_addr, cnt, n_res, lane, p.k);
           tmem_ld_wait();
         }
       drained:
@@ -703,9 +716,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         // profiles/probe_r2_v10_filter_shard8_tile_end_trigger.txt).  The mid-tile path remains for a row that overflows
         // inside a tile.  (Measured and not kept: releasing the slot before the last chunk is filtered, and giving the
         // MMA / TMA warps the highest warp ids -- both neutral: the epilogue warps' own time per tile is the limit.)
-        if (p.tile_end_trigger < kBufEntries && p.debug_mode == 0) {
+        if (p.tile_end_trigger < kBufEntries && (p.debug_mode == 0 || p.debug_mode == 9)) {
           const unsigned early = __ballot_sync(0xffffffffu, cnt > p.tile_end_trigger);
-          compact_rows(early, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+          compact_rows(early, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, n_ovf, m3, ubias, c, inv_c, ctx);
         }
         slot += 2;                          // q += 2
         if (slot >= kFAccSlots) {
@@ -715,7 +728,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
       }
 
       // end of the item range: final compaction of every row of this warp, then emit the survivors
-      compact_rows(0xffffffffu, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, m3, ubias, c, inv_c, ctx);
+      compact_rows(0xffffffffu, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, n_ovf, m3, ubias, c, inv_c,
+                   ctx);
       if (u_ok) {
         const int64_t base = u * p.n_splits + sp;
         float* os = p.cand_score + base * kKeepMax;
