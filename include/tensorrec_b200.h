@@ -118,6 +118,10 @@ int trk_score_attention_f32(const float* user_repr, const float* attention_repr,
 size_t trk_rank_full_workspace_bytes(int64_t n_users, int64_t n_items);
 int trk_rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_items, void* workspace,
                   size_t workspace_bytes, void* stream);
+/* order[ranks[i] - 1] = i for ONE row of ranks: the items of that row listed by reference rank (tf.nn.top_k order).
+ * trk_rank_full on the 1 x n_items row of item biases followed by this call is the stable descending sort that fixes the
+ * filter kernel's processing order (no library sort on the predict path). */
+int trk_order_from_ranks(const int32_t* ranks, int64_t n, int32_t* order, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K2+K3 fused (tensor cores, sm_100a)  scores and per-user top-k without materialising [n_users, n_items]

@@ -35,6 +35,7 @@ SIGNATURES = {
                                                _c_p]),
     'trk_rank_full_workspace_bytes': (_c_sz, [_c_i64, _c_i64]),
     'trk_rank_full': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_p, _c_sz, _c_p]),
+    'trk_order_from_ranks': (ctypes.c_int, [_c_p, _c_i64, _c_p, _c_p]),
     'trk_score_topk_max_k': (ctypes.c_int, [_c_i32]),
     'trk_pack_item_meta': (ctypes.c_int, [_c_p, _c_p, _c_i64, _c_p, _c_i64, _c_p]),
     'trk_score_topk_f16x3': (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i32, _c_i32, _c_i32,

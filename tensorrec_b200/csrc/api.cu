@@ -38,6 +38,7 @@ int score_f32(const float*, const float*, const float*, const float*, const floa
 int l2_normalize_rows(float*, int64_t, int32_t, cudaStream_t);
 size_t rank_full_workspace_bytes(int64_t, int64_t);
 int rank_full(const float*, int32_t*, int64_t, int64_t, void*, size_t, cudaStream_t);
+int order_from_ranks(const int32_t*, int64_t, int32_t*, cudaStream_t);
 int score_topk_max_k(int32_t);
 int score_topk_f16x3(const void*, const float*, const float*, const void*, const float*, int64_t, int64_t, int32_t,
                      int32_t, int32_t, int32_t, float*, int32_t*, const int32_t*, cudaStream_t);
@@ -125,6 +126,10 @@ size_t trk_rank_full_workspace_bytes(int64_t n_users, int64_t n_items) {
 int trk_rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_items, void* workspace,
                   size_t workspace_bytes, void* stream) {
   return trk::rank_full(scores, ranks, n_users, n_items, workspace, workspace_bytes, trk::as_stream(stream));
+}
+
+int trk_order_from_ranks(const int32_t* ranks, int64_t n, int32_t* order, void* stream) {
+  return trk::order_from_ranks(ranks, n, order, trk::as_stream(stream));
 }
 
 int trk_score_topk_max_k(int32_t d_pad) { return trk::score_topk_max_k(d_pad); }

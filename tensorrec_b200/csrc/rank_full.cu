@@ -256,4 +256,23 @@ int rank_full(const float* scores, int32_t* ranks, int64_t n_users, int64_t n_it
   return TRK_OK;
 }
 
+// order[rank - 1] = index: the permutation that lists one row's items by reference rank (the inverse of rank_full's
+// output for that row).  With the item biases as the row this is the stable descending sort the filter kernel's
+// processing order needs (tf.nn.top_k order: value descending, lower index first on ties).
+__global__ void order_from_ranks_kernel(const int32_t* __restrict__ ranks, int64_t n, int32_t* __restrict__ order) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    order[ranks[i] - 1] = static_cast<int32_t>(i);
+}
+
+int order_from_ranks(const int32_t* ranks, int64_t n, int32_t* order, cudaStream_t stream) {
+  TRK_CHECK_ARG(ranks && order && n >= 0 && n < (1ll << 31), "order_from_ranks: bad arguments");
+  if (n == 0) return TRK_OK;
+  const int64_t blocks = ceil_div(n, 256);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  order_from_ranks_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, stream>>>(ranks, n, order);
+  TRK_CHECK_LAUNCH();
+  return TRK_OK;
+}
+
 }  // namespace trk

@@ -8,6 +8,9 @@ import torch
 
 from . import _lib
 
+import os as _os
+BIAS_ORDER = _os.environ.get('TENSORREC_B200_BIAS_ORDER', 'kernel')   # 'kernel' (trk_rank_full + trk_order_from_ranks) | 'torch'
+
 TILE_ITEMS = 256     # item tile of the tensor-core kernel (item_meta is padded to a multiple of this)
 TILE_USERS = 128
 
@@ -404,7 +407,16 @@ def bias_processing_order(item_bias):
     Highest biases first: the running k-th best rises early, and every later block starts below it by its bias gap."""
     if item_bias is None:
         return None
-    return torch.sort(item_bias, descending=True, stable=True).indices.to(torch.int32)
+    if BIAS_ORDER == 'torch':
+        return torch.sort(item_bias, descending=True, stable=True).indices.to(torch.int32)
+    # own kernels: the reference ranks of the 1 x I bias row (K3: value descending, lower index first on ties), inverted
+    lib = require_cuda()
+    n = int(item_bias.numel())
+    ranks = rank_full(item_bias.contiguous().view(1, n))
+    order = torch.empty((n,), dtype=torch.int32, device=item_bias.device)
+    rc = lib.trk_order_from_ranks(_p(ranks), n, _p(order), _stream())
+    _lib.check(rc, 'trk_order_from_ranks')
+    return order
 
 
 def score_filter(user_split, user_scale, user_bias, user_norm, item_hi, item_stats, item_bias_pad, block_bias_max,
