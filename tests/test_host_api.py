@@ -390,10 +390,16 @@ def test_transposed_csr_keeps_duplicates_and_row_order():
     assert np.allclose(dense_t @ g, a.toarray().T.astype(np.float64) @ g)
 
 
-def test_bias_processing_order_is_a_stable_descending_sort():
+def test_bias_processing_order_is_a_stable_descending_sort(monkeypatch):
     """kernels.bias_processing_order: the item order the filter kernel sweeps (highest bias first, ties by lower
-    item index -> the order, and with it every result, is deterministic)."""
+    item index -> the order, and with it every result, is deterministic).  Here the library-sort form
+    (TENSORREC_B200_BIAS_ORDER=torch); the default own-kernel form is checked against the same statement on the GPU
+    (tests/test_kernels_gpu.py) and raises without a CUDA device like every other kernel call."""
     from tensorrec_b200 import kernels
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            kernels.bias_processing_order(torch.zeros(4))
+    monkeypatch.setattr(kernels, 'BIAS_ORDER', 'torch')
     rng = np.random.default_rng(11)
     bias = rng.integers(-3, 4, size=5000).astype(np.float32) * 0.25          # many exact ties
     perm = kernels.bias_processing_order(torch.from_numpy(bias))

@@ -417,6 +417,22 @@ def test_operand_stats_and_global_rescale(K):
     assert np.array_equal(bmax_p.cpu().numpy(), padded_p.cpu().numpy().reshape(-1, 128).max(axis=1))
 
 
+@pytest.mark.parametrize('n', [1, 7, 4096, 5000, 300001])
+def test_bias_processing_order_from_own_kernels(K, monkeypatch, n):
+    """trk_rank_full on the 1 x n bias row + trk_order_from_ranks == the stable descending argsort (ties by lower item
+    index, -0.0 == +0.0), and == the library-sort form."""
+    rng = np.random.default_rng(n)
+    bias = (rng.integers(-3, 4, size=n).astype(F32) * 0.25)          # many exact ties
+    if n > 10:
+        bias[3], bias[9] = -0.0, 0.0
+    assert K.BIAS_ORDER == 'kernel'
+    perm = K.bias_processing_order(dev(bias))
+    assert perm.dtype.is_floating_point is False and perm.shape == (n,)
+    assert np.array_equal(perm.cpu().numpy(), np.argsort(-bias, kind='stable'))
+    monkeypatch.setattr(K, 'BIAS_ORDER', 'torch')
+    assert np.array_equal(K.bias_processing_order(dev(bias)).cpu().numpy(), perm.cpu().numpy())
+
+
 @pytest.mark.parametrize('U,I,d,k,regime,cosine,splits', [
     (100, 150, 100, 10, 'tag', False, None), (500, 3000, 128, 10, 'indicator', False, None),
     (200, 2000, 64, 12, 'tag', True, 3), (1000, 20000, 128, 10, 'indicator', False, 1),
