@@ -241,6 +241,18 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
+def workload_config(args):
+    """`config` of the JSON line: IDENTICAL in both arms (the driver compares them); arm-specific facts go to `details`."""
+    d_pad = ((args.d + 63) // 64) * 64
+    f_users, f_items = int(args.users * 1.2), int(args.items * 1.2)
+    operands_mb = (args.users + args.items) * 2 * d_pad * 2 / 1e6
+    tables_mb = (f_users + f_items) * args.d * 4 / 1e6
+    return {'workload': workload_string(args),
+            'l2': 'split operands %.0f MB, weight tables %.0f MB against 126 MB of L2: %s'
+                  % (operands_mb, tables_mb, 'inputs exceed L2, no flush between steps needed'
+                     if min(operands_mb, tables_mb) > 126 else 'inputs FIT in L2 - a test size, not a bench line')}
+
+
 def workload_string(args):
     """config.workload: the same string in both arms (the driver compares them)."""
     scores = getattr(args, 'scores', 'iid')
@@ -546,16 +558,14 @@ def run_b200(args):
                   'split operands, fp32 accumulate)'
                   if use_filter else 'f32 (3 x fp16 split-product tcgen05 passes, fp32 accumulate)'),
         'data': 'synthetic',
-        'config': {'workload': workload_string(args),
-                   'parallelism': ('item axis sharded x%d%s: 1 NCCL all-to-all of the per-shard top-k per item group, each '
-                                   'rank merges its user slice'
-                                   % (item_shards, '' if n_groups == 1 else ' x %d user groups' % n_groups))
-                   if world > 1 else 'single GPU',
-                   'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
-                   'fallback_rows_last_step': fallback_rows, 'scores': args.scores,
-                   'fallback_overflow_whole_batch_exact': bool(last_overflow),
-                   'l2': 'inputs exceed L2 (operands %.0f MB, tables %.0f MB)'
-                   % ((n_users + n_local) * 2 * d_pad * 2 / 1e6, (wu.nbytes + wi.nbytes) / 1e6)},
+        'config': workload_config(args),
+        'details': {'parallelism': ('item axis sharded x%d%s: 1 NCCL all-to-all of the per-shard top-k per item group, '
+                                    'each rank merges its user slice'
+                                    % (item_shards, '' if n_groups == 1 else ' x %d user groups' % n_groups))
+                    if world > 1 else 'single GPU',
+                    'n_splits': n_splits, 'topk_path': 'filter+rescore' if use_filter else 'exact3',
+                    'fallback_rows_last_step': fallback_rows, 'scores': args.scores,
+                    'fallback_overflow_whole_batch_exact': bool(last_overflow)},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'ms_per_step': e2e_ms_step, 'api': 'TensorRec.predict_rank(user_features, item_features, k) on pinned '
@@ -637,7 +647,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_string(args)},
+        'config': workload_config(args),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': desc + ' -- numpy/scipy restatement of the reference TF-CPU semantics (TensorFlow is '
                          'not installable here); each step is a bounded user sample of the workload, ms_per_step is the '

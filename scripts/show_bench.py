@@ -10,7 +10,7 @@ for path in sys.argv[1:]:
         continue
     print('%s: n_gpus %s  ms/step %.2f  value %.3e  e2e %.2f ms (%.3e)  filter frac %.3f  fallback %s' % (
         path, d.get('n_gpus'), d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['e2e']['value'],
-        d['roofline']['frac'], d['config'].get('fallback_rows_last_step')))
+        d['roofline']['frac'], d.get('details', d['config']).get('fallback_rows_last_step')))
     ph = d.get('phases_ms', {})
     for key in ('rank0', 'max_over_ranks', 'mean_over_ranks'):
         if key in ph and isinstance(ph[key], dict):
