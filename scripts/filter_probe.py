@@ -72,7 +72,7 @@ pairs = A.users * float(A.items)
 print('shape %d users x %d items, d=%d' % (A.users, A.items, A.d))
 if os.environ.get('PROBE_COOL'):
     print('single launches after idle (high clocks): full kernel %.2f ms' % timeit_cool(run_filter))
-    for mode in ('9', '4', '1', '2', '6'):
+    for mode in ('4', '1', '2', '6'):
         os.environ['TRK_FILTER_DEBUG'] = mode
         print('  cool debug=%s: %.2f ms' % (mode, timeit_cool(run_filter)))
     os.environ['TRK_FILTER_DEBUG'] = '0'

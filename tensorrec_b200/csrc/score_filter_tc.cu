@@ -53,6 +53,7 @@ constexpr int kFilterMaxK = 12;
 constexpr float kMarginFactor = 1.5f * 0.0009765625f;   // 1.5 * 2^-10
 constexpr float kBiasUlps = 4.0f * 1.1920929e-7f;        // 4 ulp(1): rounding of (dot + ub) + ib
 constexpr float kThetaMargins = 2.25f;                   // theta = a_k - 2.25 m  (> 2 m is what the proof needs)
+constexpr int kTileEndMaxTiles = 3072;   // sweeps of up to 393216 items per split run the tile-end compaction variant
 constexpr int kGiveUpOverflows = 8;   // a row whose compactions overflow this often is handed to the exact kernel
 
 struct FilterParams {
@@ -76,9 +77,11 @@ struct FilterParams {
   int32_t n_tiles;
   int32_t n_user_pairs;        // ceil(n_users / 256)
   int32_t item_id_offset;
-  int32_t tile_end_trigger;    // rows holding more entries than this are compacted at the END of a tile (see the epilogue)
+  int32_t tile_end_trigger;    // kTileEnd kernels: rows holding more entries than this are compacted at the END of a tile
   int32_t debug_mode;          // timing experiments only (TRK_FILTER_DEBUG): 1 = drain TMEM without filtering, 2 = no drain,
                                // 4 = nothing admitted, 6 = MMA only (no B stream, no drain), 7 = full kernel + clock readout
+                               // (9, "filter half of every tile's columns", was a build-time experiment: its run-time
+                               // loop bound cost 2.5 % at 1M items -- profiles/probe_r2_v18_filter_ab_full.txt)
   float* cand_score;           // [n_users, n_splits, kKeepMax] approximate scores (sentinel -inf)
   int32_t* cand_item;          // [n_users, n_splits, kKeepMax] global ids (sentinel INT32_MAX)
   float* row_theta;            // [n_users, n_splits] final admission threshold (certified by rescore_topk_kernel)
@@ -425,7 +428,11 @@ __device__ long long g_filter_debug_clock[2];   // {SM cycles, ns} of CTA 0, wri
 // 256-user groups over the SAME item tiles: each CTA fetches half of every tile and TMA-multicasts it into both CTAs'
 // shared memory, so the L2 -> SM stream of the item operand (1 TB per launch at 1M x 1M x d128, the second largest
 // consumer after the MMAs) is halved.
-template <int kNKB, int kCluster>
+// kTileEnd: compile the tile-end compaction pass in (see the epilogue).  It pays for short sweeps, where the admission
+// path is a large share of the time, and costs at long ones -- mostly through what its second inlined copy of the
+// compaction does to the hot loop's code, so it is a template parameter and not a run-time switch
+// (profiles/probe_r2_v18_filter_ab_*.txt: 125K items 32.35 -> 31.7 ms with it, 1M items 205.6 -> 209.3 ms).
+template <int kNKB, int kCluster, bool kTileEnd>
 __global__ void __launch_bounds__(kFThreads, 1)
 score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -643,7 +650,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tcgen05_fence_after();
         const uint32_t taddr = tmem_lane + kFTmemAccCol + slot * kFBlockN;
         const int32_t pos0 = t * kFBlockN;
-        if (t == t0 && p.block_bias_min != nullptr && (p.debug_mode == 0 || p.debug_mode == 9)) {
+        if (t == t0 && p.block_bias_min != nullptr && p.debug_mode == 0) {
           const float bmin = __ldg(p.block_bias_min + t0);   // the same for the whole CTA: warp-uniform branch
           if (bmin > kNegInf) {
             float g[16];
@@ -692,12 +699,12 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         tmem_ld_32x32b_x32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll 1
-        for (int ch = 0; ch < (p.debug_mode == 9 ? 2 : kFBlockN / 32); ch += 2) {   // 9: timing experiment, half the columns
+        for (int ch = 0; ch < kFBlockN / 32; ch += 2) {   // (compile-time bounds: a run-time bound here cost 2.5 %)
           tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while chunk ch is filtered
           filter_32(ra, pos0 + ch * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3, buf_row_addr,
                     cnt, n_res, lane, p.k);
           tmem_ld_wait();
-          if (ch + 2 < (p.debug_mode == 9 ? 2 : kFBlockN / 32)) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
+          if (ch + 2 < kFBlockN / 32) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
           filter_32(rb, pos0 + (ch + 1) * 32, bmax_scaled, ctx, c, inv_c, ubias, tau, theta, drop_max, n_ovf, m3,
                     buf_row_addr, cnt, n_res, lane, p.k);
           tmem_ld_wait();
@@ -714,9 +721,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap map_items, const FilterP
         // buffer is filling up are compacted HERE, after the slot has gone back to the MMA warp: the round trip overlaps
         // the MMAs of this group's next accumulator (-1.5 ms of 32 at the shard with the trigger at 26 of 32 entries,
         // profiles/probe_r2_v10_filter_shard8_tile_end_trigger.txt).  The mid-tile path remains for a row that overflows
-        // inside a tile.  (Measured and not kept: releasing the slot before the last chunk is filtered, and giving the
+        // inside a tile.  Compiled in only for kTileEnd (short sweeps; see the template parameter).  (Measured and not kept: releasing the slot before the last chunk is filtered, and giving the
         // MMA / TMA warps the highest warp ids -- both neutral: the epilogue warps' own time per tile is the limit.)
-        if (p.tile_end_trigger < kBufEntries && (p.debug_mode == 0 || p.debug_mode == 9)) {
+        if (kTileEnd && p.debug_mode == 0) {
           const unsigned early = __ballot_sync(0xffffffffu, cnt > p.tile_end_trigger);
           compact_rows(early, buf_row_addr, lane, p.k, cnt, n_res, theta, tau, drop_max, n_ovf, m3, ubias, c, inv_c, ctx);
         }
@@ -947,9 +954,17 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
   p.tiles_per_split = static_cast<int32_t>(ceil_div(p.n_tiles, n_splits));
   p.n_user_pairs = static_cast<int32_t>(ceil_div(n_users, 2 * kFBlockM));
   p.item_id_offset = item_id_offset;
+  // Tile-end compaction for sweeps of up to kTileEndMaxTiles item tiles per split (measured: helps at 125K items,
+  // costs at 1M; the crossover interpolates to ~380K).  TRK_FILTER_TILE_END_TRIGGER (probe knob): a value below
+  // kBufEntries forces it on with that trigger, kBufEntries or more forces it off.
+  bool tile_end = p.tiles_per_split <= kTileEndMaxTiles;
+  p.tile_end_trigger = 26;
   {
-    const char* env = getenv("TRK_FILTER_TILE_END_TRIGGER");   // probe knob; kBufEntries (32) switches the tile-end pass off
-    p.tile_end_trigger = env != nullptr ? atoi(env) : 26;
+    const char* env = getenv("TRK_FILTER_TILE_END_TRIGGER");
+    if (env != nullptr) {
+      tile_end = atoi(env) < kBufEntries;
+      if (tile_end) p.tile_end_trigger = atoi(env);
+    }
     if (p.tile_end_trigger < kKeepMax + 2) p.tile_end_trigger = kKeepMax + 2;   // (a compaction leaves up to kKeepMax)
   }
   p.cand_score = cand_score;
@@ -977,8 +992,10 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     const char* env = getenv("TRK_FILTER_CLUSTER");
     if (env != nullptr && (atoi(env) == 1 || atoi(env) == 2)) cluster = atoi(env);
   }
-  auto kernel2 = p.n_kblocks == 2 ? score_filter_kernel<2, 2> : score_filter_kernel<1, 2>;
-  auto kernel1 = p.n_kblocks == 2 ? score_filter_kernel<2, 1> : score_filter_kernel<1, 1>;
+  auto kernel2 = tile_end ? (p.n_kblocks == 2 ? score_filter_kernel<2, 2, true> : score_filter_kernel<1, 2, true>)
+                          : (p.n_kblocks == 2 ? score_filter_kernel<2, 2, false> : score_filter_kernel<1, 2, false>);
+  auto kernel1 = tile_end ? (p.n_kblocks == 2 ? score_filter_kernel<2, 1, true> : score_filter_kernel<1, 1, true>)
+                          : (p.n_kblocks == 2 ? score_filter_kernel<2, 1, false> : score_filter_kernel<1, 1, false>);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   int max_clusters = 0;
@@ -995,11 +1012,11 @@ int score_filter_f16(const void* user_split, const float* user_scale, const floa
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // the answer depends on (device, kernel, shared memory) only: asked once per device and kernel variant
-    static int cached_clusters[64][2];
-    static bool cached_valid[64][2];
+    static int cached_clusters[64][4];
+    static bool cached_valid[64][4];
     int device = 0;
     TRK_CHECK_CUDA(cudaGetDevice(&device));
-    const int variant = p.n_kblocks == 2 ? 1 : 0;
+    const int variant = (p.n_kblocks == 2 ? 1 : 0) + (tile_end ? 2 : 0);
     if (device >= 0 && device < 64 && cached_valid[device][variant]) {
       max_clusters = cached_clusters[device][variant];
     } else {

@@ -602,6 +602,28 @@ def test_filter_cluster_pairs_with_splits_and_a_ragged_last_tile(K, monkeypatch)
             assert (got_i != exp_i).mean() < 0.01
 
 
+@pytest.mark.parametrize('cluster', ['1', '2'])
+def test_filter_variants_with_and_without_the_tile_end_pass_agree(K, monkeypatch, cluster):
+    """The launch picks one of two compiled forms by sweep length (tile-end compaction for up to 3072 tiles per split);
+    the probe knob forces either on any shape: same certified result, bit for bit, and equal to the oracle's."""
+    monkeypatch.setenv('TRK_FILTER_CLUSTER', cluster)
+    for (U, I, d, k, splits) in [(700, 40000, 128, 10, 1), (300, 9000, 64, 12, 2)]:
+        uf, itf, wu, wi, bu, bi = make_case(U, I, d, False, seed=I, regime='indicator')
+        got = {}
+        for name, trigger in (('default', None), ('tile_end', '20'), ('plain', '32')):
+            if trigger is None:
+                monkeypatch.delenv('TRK_FILTER_TILE_END_TRIGGER', raising=False)
+            else:
+                monkeypatch.setenv('TRK_FILTER_TILE_END_TRIGGER', trigger)
+            got[name] = run_filter(K, uf, itf, wu, wi, bu, bi, k, n_splits=splits)
+        for name in ('tile_end', 'plain'):
+            assert np.array_equal(got[name][1], got['default'][1]) and np.array_equal(got[name][0], got['default'][0])
+        scores = oracle_scores(uf, itf, wu, wi, bu, bi)
+        model = oracle.OracleModel([wu], wi, bu, bi)
+        tol = H.norm_tolerance(model.user_representation(uf)[0], model.item_representation(itf)) + 2e-6
+        check_float_topk(scores, tol, got['plain'][0], got['plain'][1], k)
+
+
 def test_filter_infinite_item_biases_stay_nan_free(K):
     """-inf biases (items that must never be recommended) and a few +inf ones: no NaN reaches the result, the +inf
     items lead every list in id order, no -inf item is returned while finite ones remain."""
