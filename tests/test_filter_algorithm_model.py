@@ -9,11 +9,13 @@ import pytest
 BUF, KEEP, MARGINS = 32, 16, 2.25
 
 
-def run_row(exact, approx, bias_order_pos, block_max_of, m, k, block=128, step=16):
+def run_row(exact, approx, bias_order_pos, block_max_of, m, k, block=128, step=16, theta_init=-np.inf, raw=False):
     """One user row.  exact/approx: per-item scores (approx within m of exact); processing order = bias_order_pos.
-    block_max_of(pos) -> admission slack of the block (>= 0): the bound test admits a superset of approx > tau."""
+    block_max_of(pos) -> admission slack of the block (>= 0): the bound test admits a superset of approx > tau.
+    theta_init: a threshold the row starts from (section "shared thresholds" below); raw=True returns the survivors
+    and the row's final threshold instead of the certified top-k."""
     n = len(exact)
-    theta, tau, drop_max = -np.inf, -np.inf, -np.inf
+    theta, tau, drop_max = theta_init, theta_init, -np.inf
     buf = []                                           # [(approx score, item id)]
 
     def compact():
@@ -25,6 +27,7 @@ def run_row(exact, approx, bias_order_pos, block_max_of, m, k, block=128, step=1
             if len(kept) > KEEP:
                 drop_max = max(drop_max, kept[KEEP][0])
                 kept = kept[:KEEP]
+            floor = max(floor, theta)                  # (a carried threshold is never lowered)
             buf, theta, tau = kept, floor, floor       # (the kernel lowers tau by a few ulps: more admissions only)
         # fewer than k entries: nothing can be dropped yet
 
@@ -38,6 +41,8 @@ def run_row(exact, approx, bias_order_pos, block_max_of, m, k, block=128, step=1
         assert len(buf) <= BUF
     compact()
     row_theta = max(theta, drop_max)
+    if raw:
+        return [i for _, i in buf], row_theta, theta
     # rescore_topk_kernel: exact scores of the survivors, tf.nn.top_k order, certificate
     surv = sorted(((exact[i], i) for _, i in buf), key=lambda e: (-e[0], e[1]))
     top = surv[:k]
@@ -104,3 +109,61 @@ def test_overflow_of_near_ties_is_never_silently_wrong():
     approx = exact + np.linspace(-m, m, n)
     top, certified = run_row(exact, approx, np.arange(n), lambda b: 0.0, m, k)
     assert not certified
+
+
+# ---- shared thresholds across item shards (the design the admission model argues for) ---------------
+# A shard only has to keep the items that can reach the GLOBAL top-k.  A row may therefore start a shard's sweep from
+# any theta for which k items with approximate score >= theta + 2.25 m exist SOMEWHERE (here: the threshold the row
+# ended the previous shards with, carried round a ring).  The per-shard list is then no longer the shard's own top-k,
+# so the certificate moves after the merge: exact k-th best of the union > max over shards of (theta_r, dropped_r) + m.
+def run_sharded_row(exact, approx, shards, m, k, rng):
+    theta, union, row_thetas = -np.inf, [], []
+    for ids in shards:
+        order = rng.permutation(len(ids))
+        surv, row_theta, theta_out = run_row(exact[ids], approx[ids], order, lambda b: 0.0, m, k, theta_init=theta,
+                                             raw=True)
+        union += [int(ids[i]) for i in surv]
+        row_thetas.append(row_theta)
+        theta = max(theta, theta_out)
+    merged = sorted(((exact[i], i) for i in union), key=lambda e: (-e[0], e[1]))[:k]
+    bound = max(row_thetas)
+    certified = len(merged) >= k and (bound == -np.inf or bound + m < merged[k - 1][0])
+    return [i for _, i in merged], certified, len(union)
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_carried_thresholds_keep_the_certificate_sound(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n, n_shards = int(rng.integers(600, 4000)), int(rng.integers(2, 9))
+    k = int(rng.integers(1, 13))
+    kind = seed % 4
+    if kind == 0:
+        exact = rng.standard_normal(n)
+    elif kind == 1:
+        exact = rng.integers(-2, 3, n).astype(np.float64)                     # massive ties
+    elif kind == 2:
+        exact = np.concatenate([rng.standard_normal(n - 30) - 5.0, np.full(30, 1.0)])
+        exact = exact[rng.permutation(n)]                                     # a plateau at the k-th place, spread over shards
+    else:
+        exact = 1.0 + 1e-4 * rng.standard_normal(n)                           # near-ties inside the error bound
+    m = 1e-3 if kind != 1 else 0.0
+    approx = exact + (np.where(rng.random(n) < 0.5, m, -m) if kind == 3 else rng.uniform(-m, m, n) if m > 0 else 0.0)
+    cuts = np.sort(rng.choice(np.arange(1, n), n_shards - 1, replace=False))
+    shards = np.split(np.arange(n), cuts)
+    top, certified, n_union = run_sharded_row(exact, approx, shards, m, k, rng)
+    if certified:
+        assert top == exact_topk(exact, k)
+
+
+def test_carried_thresholds_shrink_the_lists_and_still_certify_clear_rows():
+    rng = np.random.default_rng(5)
+    n, k, m, n_shards = 16000, 10, 1e-4, 8
+    exact = rng.standard_normal(n)
+    approx = exact + rng.uniform(-m, m, n)
+    shards = np.split(np.arange(n), n_shards)
+    top, certified, n_union = run_sharded_row(exact, approx, shards, m, k, rng)
+    assert certified and top == exact_topk(exact, k)
+    # every shard on its own keeps between k and 16 survivors (8 k ... 128 in total); with a carried threshold a later
+    # shard keeps only what beats the k-th best seen so far (theta alone is carried, not the lists: it rises only when a
+    # shard finds k better items by itself, so this is an upper bound on what the design sends through the exchange)
+    assert n_union < 8 * k
