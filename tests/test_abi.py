@@ -66,3 +66,20 @@ def test_no_cpu_fallback_without_a_cuda_device():
     q = ctypes.cast(idx, ctypes.c_void_p)
     rc = lib.trk_csr_project_biases_f32(q, q, p, p, 2, p, None)
     assert rc == _lib.TRK_ERR_CUDA
+
+
+def test_integration_stub_argtypes_match_the_binding_table():
+    """The ctypes stub INTEGRATION.md shows a maintainer of the reference must agree with the shipped table."""
+    import ctypes
+    import re
+    from tensorrec_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'INTEGRATION.md')).read()
+    env = {'_p': ctypes.c_void_p, '_i32': ctypes.c_int32, '_i64': ctypes.c_int64, 'ctypes': ctypes}
+    found = re.findall(r'^_lib\.(trk_\w+)\.argtypes = (.+)$', text, flags=re.M)
+    assert len(found) >= 10
+    for name, expr in found:
+        shown = eval(expr, env)
+        shipped = _lib.SIGNATURES[name][1]
+        assert len(shown) == len(shipped), name
+        for a, b in zip(shown, shipped):
+            assert ctypes.sizeof(a) == ctypes.sizeof(b) and (a is ctypes.c_void_p) == (b is ctypes.c_void_p), name
